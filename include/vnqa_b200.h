@@ -1,0 +1,180 @@
+/*
+ * vnqa_b200.h - C ABI of libvnqa_b200.so: hand-written sm_100a kernels for the VideoNavQA FiLM hot path.
+ *
+ * The reference (catalina17/VideoNavQA) is pure PyTorch: it has no FFI of its own.  The entry points below
+ * are what its nn.Module forward/backward for this path bind to, one per op group; each comment cites the
+ * reference lines (relative to the reference root) the call replaces.  All pointers are DEVICE pointers;
+ * `stream` is a cudaStream_t passed as void*.  No torch types cross this boundary.  Every function returns 0 on
+ * success or a negative code (-1 bad argument, -2 CUDA error, -3 tensor-map error); vnqa_last_error() gives the
+ * thread-local message.  The library allocates no device memory: callers own every buffer.
+ *
+ * Activation layout ("frame-image major NHWC"): a batch of clips is flattened to n_img = sum(v_lens) frame
+ * images ordered frame-major (all clips of frame 0, then frame 1, ...; clips sorted by descending length as
+ * the reference requires, models/film_attn_pt_stem.py:184-186), each image stored as [10][13][C] fp32.
+ * Tensors that feed a tensor-core MMA hold tf32-representable values (rounded to nearest by their producer).
+ */
+#ifndef VNQA_B200_H
+#define VNQA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNQA_ABI_VERSION 1
+#define VNQA_IMG_H 10
+#define VNQA_IMG_W 13
+#define VNQA_IMG_PIX 130 /* hard-coded 130 = 10*13 in models/film_attn_pt_stem.py:56 */
+
+int vnqa_abi_version(void);
+const char* vnqa_last_error(void);
+/* 0 iff the current CUDA device is sm_100 (B200); the product path has no other backend. */
+int vnqa_device_check(void);
+int vnqa_sm_count(void);
+
+/* ---- K0: (B, C, 10, 13, T) fp32, T innermost  ->  frame-image-major NHWC [n_img][130][C].
+ * Replaces the strided slice v_input[:ct, :, :, :, i] (models/film_attn_pt_stem.py:210).
+ * img_of[b*T + t] is the image index of (clip b, frame t), or -1 when t >= v_lens[b]. */
+int vnqa_frames_to_nhwc(const float* v_input, float* x_out, const int32_t* img_of, int32_t B, int32_t C, int32_t T,
+                        void* stream);
+/* (no backward: v_input needs no gradient - the stem is frozen, eval/q_and_v_eval.py:101-110) */
+
+/* ---- weight packing (derived caches; PyTorch-native layouts stay the source of truth).
+ * conv weight (Cout, Cin, kh, kw) -> [taps][rows_pad][Cin] K-major rows (zero rows for cout..rows_pad).
+ * transpose_flip != 0 builds the data-gradient operand instead: [taps][rows_pad >= Cin][Cout] with taps mirrored. */
+int vnqa_pack_conv_weight(const float* w, float* packed, int32_t cout, int32_t cin, int32_t taps,
+                          int32_t rows_pad, int32_t transpose_flip, void* stream);
+/* Linear weight (N, C*130) in NCHW-flatten order (col = c*130 + p, models/film_attn_pt_stem.py:244) ->
+ * (n_pad, 130*C) in NHWC order (col = p*C + c); inverse != 0 maps a gradient (n rows) back. */
+int vnqa_permute_fc_weight(const float* w, float* out, int32_t n, int32_t n_pad, int32_t C, int32_t inverse,
+                           void* stream);
+
+/* ---- K1/K2/K3: implicit-GEMM convolution / GEMM on tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM).
+ * D[co][pixel] = sum_{tap,ci} Wp[tap][co][ci] * X[pixel + tap][ci], 128 x 208 tiles (208 = 8 images x 2 rows x 13),
+ * operands staged by TMA (the zero halo is the TMA out-of-bounds fill), fused epilogues below. */
+enum {
+  VNQA_EPI_BIAS_RELU = 0,        /* out = relu(acc + bias)                       conv1x1 skip (:219), gp tail (gp :228) */
+  VNQA_EPI_BIAS_RELU_AFFINE = 1, /* out = relu(acc + bias) * scale + shift       conv_init + BN eval (:211) */
+  VNQA_EPI_BIAS_RELU_STATS = 2,  /* out = relu(acc + bias); per-(frame,ch) sum/sumsq  conv_init + BN train (:211) */
+  VNQA_EPI_FILM = 3,             /* z = acc + bias; out = relu(a*z + b) + res    ResBlock body (:224-241) */
+  VNQA_EPI_PARTIAL = 4,          /* out[split][row][co] = acc                    split-K GEMM (fc_embed_attn :244) */
+  VNQA_EPI_DGRAD_RES = 5,        /* out = (acc + add) * [mask > 0]               dX of conv3x3 + skip, through ReLU (:219) */
+  VNQA_EPI_PLAIN = 7             /* out = acc                                    dX of conv1x1 / Linear */
+};
+
+typedef struct {
+  /* operands */
+  const float* w_packed; /* [taps][rows_pad][cin] from vnqa_pack_conv_weight (flat: [rows_pad][cin*splits]) */
+  const float* x;        /* activations [n_img][130][cin] (conv) or [n_img][x_ld] (flat) */
+  int32_t taps;          /* 1 or 9 */
+  int32_t cin;           /* reduction length per tap (per split when flat); multiple of 32 */
+  int32_t cout;          /* real output channels */
+  int32_t rows_pad;      /* cout rounded up to 128 */
+  int32_t n_img;         /* conv: images; flat: rows of x */
+  int32_t flat;          /* 0: conv over 10x13 images; 1: plain GEMM */
+  int32_t x_ld;          /* flat only: row stride of x in floats (>= cin*splits) */
+  int32_t splits;        /* flat only: split-K factor */
+  int32_t epi;
+  int32_t no_round;      /* != 0: store full fp32 (output does not feed an MMA) */
+  /* epilogue operands (unused ones may be NULL) */
+  float* out;            /* [rows][cout] (PARTIAL: [splits][n_img][cout]) */
+  const float* bias;     /* [cout] */
+  const float* scale;    /* AFFINE: [cout] */
+  const float* shift;    /* AFFINE: [cout] */
+  const int32_t* img_frame; /* STATS: frame of each image */
+  double* stat_sum;      /* STATS: [T][cout], atomically accumulated */
+  double* stat_sq;       /* STATS: [T][cout] */
+  const float* film;     /* FILM: film values, row r at film + r*film_ld */
+  const int32_t* film_row; /* FILM: row of `film` for each image (= frame*B + clip) */
+  int32_t film_ld;
+  int32_t alpha_off;     /* FILM: alpha at [alpha_off + co], beta at [alpha_off + cout + co] */
+  const float* res;      /* FILM: residual input [rows][cout]; DGRAD_RES: ReLU mask source */
+  float* z_out;          /* FILM: optional pre-FiLM output z (training) */
+  const float* add;      /* DGRAD_RES: tensor added before masking (skip-path gradient) */
+  float* dbias;          /* DGRAD_RES: optional per-channel sum of the written gradient, atomically accumulated */
+} vnqa_conv_args;
+
+int vnqa_conv_gemm(const vnqa_conv_args* args, void* stream);
+
+/* ---- K4: weight gradient dW[co][ci][tap] += sum_rows dY[row][co] * X[row (+) tap][ci] on tcgen05 (MN-major
+ * operands, split-K over pixels, fp32 atomic reduction).  dw must be zero-initialised; layout is PyTorch's
+ * (Cout, Cin, kh, kw).  flat != 0: plain dY^T X with dy [n_img][cout], x [n_img][cin]. */
+int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32_t n_img, int32_t cout, int32_t cin,
+                    int32_t taps, int32_t flat, void* stream);
+
+/* ---- small fp32 GEMM (FFMA, exact fp32): C = [C +] A B^T + bias, optional ReLU.  A(m,k) = a[m*a_rs + k*a_cs],
+ * B(n,k) = b[n*b_rs + k*b_cs].  ksplit > 1 splits K over gridDim.z with atomic accumulation into C (C must be
+ * zero-initialised or hold the value to accumulate onto; relu/bias are then not allowed).
+ * Linears of :179 (FiLM generator), :301 (classifier) and their gradients. */
+int vnqa_sgemm(const float* a, const float* b, float* c, const float* bias, int32_t M, int32_t N, int32_t K,
+               int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int64_t ldc, int32_t relu, int32_t accumulate,
+               int32_t ksplit, void* stream);
+/* out[n] (+)= sum_rows x[row][n] */
+int vnqa_colsum(const float* x, int32_t rows, int32_t n, int64_t ld, float* out, int32_t accumulate, void* stream);
+
+/* ---- BatchNorm2d after ReLU, one call per processed frame in the reference (:211, quirk Q6) */
+int vnqa_bn_finalize_train(const double* stat_sum, const double* stat_sq, const int32_t* frame_ct, int32_t n_frames,
+                           int32_t C, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                           float momentum, float eps, float* scale, float* shift, float* mean, float* rstd,
+                           void* stream);
+int vnqa_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float eps, int32_t C, float* scale, float* shift, void* stream);
+/* x = y * scale[frame] + shift[frame]   (scale/shift are [T][C]) */
+int vnqa_bn_apply(const float* y, float* x, const int32_t* img_frame, const float* scale, const float* shift,
+                  int32_t n_img, int32_t C, void* stream);
+/* dy = BN-backward(dx) masked by the preceding ReLU (y > 0); dbias += sum dy; dgamma/dbeta accumulated. */
+int vnqa_bn_backward(const float* dx, const float* y, const int32_t* img_frame, const int32_t* frame_ct,
+                     int32_t n_frames, const float* mean, const float* rstd, const float* gamma, int32_t n_img,
+                     int32_t C, float* s1, float* s2, float* dy, float* dbias, float* dgamma, float* dbeta,
+                     void* stream);
+
+/* ---- FiLM backward (autograd of :229-239): dz = alpha * dout * [alpha z + beta > 0]; dfilm rows get
+ * dalpha/dbeta (already masked by the generator's ReLU: zero where alpha/beta == 0); dbias += sum dz. */
+int vnqa_film_backward(const float* dout, const float* z, const float* film, const int32_t* film_row, int32_t film_ld,
+                       int32_t alpha_off, int32_t n_img, int32_t C, float* dz, float* dfilm, float* dbias,
+                       void* stream);
+
+/* out[dst_row[r]][n] = bias[n] + sum_s partial[s][r][n] */
+int vnqa_splitk_reduce(const float* partial, int32_t splits, int32_t rows, int32_t N, const float* bias,
+                       const int32_t* dst_row, float* out, void* stream);
+/* out[r][:] = src[src_row[r]][:] */
+int vnqa_gather_rows(const float* src, const int32_t* src_row, int32_t rows, int32_t N, float* out, void* stream);
+
+/* ---- global temporal max pooling (models/film_global_pooling_pt_stem.py:230-235) */
+int vnqa_gp_maxpool(const float* y, const int32_t* img_of, int32_t B, int32_t T, int32_t tail, float* pooled,
+                    int32_t* arg_img, void* stream);
+int vnqa_gp_maxpool_backward(const float* dpooled, const float* pooled, const int32_t* arg_img, int32_t B, int32_t tail,
+                             float* dy, void* stream);
+
+/* ---- K6: question encoder (compute_film_values, :144-171): gx = W_ih embed(q) + b_ih + b_hh once, then the
+ * packed LSTM chained over n_pass frames with carried state (quirk Q3). */
+int vnqa_embed_gates(const int64_t* q_input, const int32_t* q_lens, const float* embed, const float* w_ih,
+                     const float* b_ih, const float* b_hh, int32_t B, int32_t L, int32_t E, int32_t H, float* gx,
+                     void* stream);
+int vnqa_lstm_chain_forward(const float* gx, const int32_t* q_lens, const float* whh_t, float* h_state, float* c_state,
+                            int32_t n_pass, int32_t B, int32_t L, int32_t H, float* h_pass, float* save_gates,
+                            float* save_c, float* save_hprev, void* stream);
+int vnqa_lstm_chain_backward(const float* dh_pass, const int32_t* q_lens, const float* whh, const float* save_gates,
+                             const float* save_c, const float* c0, int32_t n_pass, int32_t B, int32_t L, int32_t H,
+                             float* dgates, float* dgx, void* stream);
+/* dembed[q[b][t]][:] += dx[b][t][:] for t < q_len[b]  (dembed pre-initialised by the caller) */
+int vnqa_embed_backward(const int64_t* q_input, const int32_t* q_lens, const float* dx, int32_t B, int32_t L, int32_t E,
+                        float* dembed, void* stream);
+int vnqa_embed_gather(const int64_t* q_input, const int32_t* q_lens, const float* embed, int32_t B, int32_t L,
+                      int32_t E, float* x, void* stream);
+
+/* ---- K7: temporal attention read-out (:253-295) and its backward */
+int vnqa_attn_tail_forward(const float* feats, const int32_t* v_lens, int32_t n_proc, int32_t B, int32_t T, int32_t A,
+                           const float* w1, const float* b1, const float* wh, const float* bh, const float* wih_t,
+                           const float* whh_t, const float* b_ih, const float* b_hh, float* hs, float* coefs,
+                           float* ctxt, float* gates, float* cs, void* stream);
+int vnqa_attn_tail_backward(const float* feats, const int32_t* v_lens, int32_t n_proc, int32_t B, int32_t T, int32_t A,
+                            const float* w1, const float* wh, const float* wih, const float* whh, const float* hs,
+                            const float* coefs, const float* gates, const float* cs, const float* dhs, float* dfeats,
+                            float* dgates, float* dw1, float* db1, float* dwh, float* dbh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+// Library-wide C-ABI plumbing: error string, device check, tensor-map encoding.
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+
+namespace vnqa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return -3;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[5];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace vnqa
+
+extern "C" int vnqa_abi_version(void) { return VNQA_ABI_VERSION; }
+extern "C" const char* vnqa_last_error(void) { return vnqa::g_err; }
+
+extern "C" int vnqa_sm_count(void) {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    vnqa::set_error("cudaGetDevice failed");
+    return -2;
+  }
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      vnqa::set_error("cudaDeviceGetAttribute failed");
+      return -2;
+    }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+extern "C" int vnqa_device_check(void) {
+  int dev = 0, major = 0, minor = 0;
+  VNQA_CHECK_CUDA(cudaGetDevice(&dev));
+  VNQA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  VNQA_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  VNQA_REQUIRE(major == 10 && minor == 0, "libvnqa_b200 needs an sm_100 device (B200); found sm_%d%d", major, minor);
+  return 0;
+}

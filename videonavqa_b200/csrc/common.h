@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/vnqa_b200.h"
+
+namespace vnqa {
+
+void set_error(const char* fmt, ...);
+
+#define VNQA_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::vnqa::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+#define VNQA_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      ::vnqa::set_error(__VA_ARGS__); \
+      return -1;                     \
+    }                                \
+  } while (0)
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+// fp32 tensor map with 128-byte swizzle and zero out-of-bounds fill. dims/strides innermost first;
+// strides in bytes for dims 1..rank-1.
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace vnqa

@@ -1,0 +1,226 @@
+// K4: weight gradients on tcgen05 tensor cores (autograd of the convolutions / Linear of
+// models/film_attn_pt_stem.py:211,219,224,244).
+//
+//   dW[tap][co][ci] = sum_{pixel rows r} dY[r][co] * X[r (+) tap][ci]
+//
+// The reduction runs over PIXELS, and both operands are stored pixel-major ([row][channel], channel contiguous),
+// i.e. "MN-major" for the MMA: no transposed copies are made - the UMMA descriptors are built MN-major
+// (instruction-descriptor bits 15/16) over 128-byte-swizzled TMA boxes {32 channels x 104 pixel rows}
+// (104 = 4 images x 2 image rows x 13 = 13 MMA K-steps of 8).  Tap shifts and the zero halo are again TMA box
+// coordinates / out-of-bounds fill.  Tile = 128 (co) x 128 (ci) fp32 accumulators in TMEM, 2 smem stages of
+// 104 KB, split-K over pixel chunks to fill 148 SMs; partial tiles are reduced with fp32 red.global.add into the
+// zero-initialised gradient, written directly in PyTorch (Cout, Cin, kh, kw) layout.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vnqa {
+
+constexpr int WG_M = 128, WG_N = 128;
+constexpr int WG_KP = 104;                       // pixel rows per stage
+constexpr int WG_BOX_BYTES = WG_KP * 128;        // 13312: one {32 ch x 104 rows} box
+constexpr int WG_A_BYTES = (WG_M / 32) * WG_BOX_BYTES;  // 53248
+constexpr int WG_B_BYTES = (WG_N / 32) * WG_BOX_BYTES;  // 53248
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES; // 106496
+constexpr int WG_STAGES = 2;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_THREADS = 256;
+constexpr int WG_TMEM_COLS = 256;                // 2 accumulator stages x 128 columns
+
+struct WParams {
+  int taps, m_tiles, n_tiles, splits, n_chunks, chunks_per_split, flat;
+  int cout, cin;          // real sizes (tiles beyond are skipped on store)
+  long long out_co_stride, out_ci_stride;  // element strides of the output for (co, ci); tap stride is 1
+  float* out;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* acc_full = empty_bar + WG_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.taps * p.splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, WG_TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (mt, nt, tap, split); mt fastest so that concurrently running CTAs share the X (B) slab in L2
+  auto decode = [&](int tile, int& mt, int& nt, int& tap, int& sp) {
+    mt = tile % p.m_tiles; tile /= p.m_tiles;
+    nt = tile % p.n_tiles; tile /= p.n_tiles;
+    tap = tile % p.taps;   sp = tile / p.taps;
+  };
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int mt, nt, tap, sp;
+      decode(tile, mt, nt, tap, sp);
+      int dy = 0, dx = 0;
+      if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+      const int c_begin = sp * p.chunks_per_split;
+      const int c_end = min(c_begin + p.chunks_per_split, p.n_chunks);
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * WG_STAGE_BYTES;
+          uint8_t* sb = sa + WG_A_BYTES;
+          mbar_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
+          int a1, a2, a3, b1, b2, b3;
+          if (p.flat) { a1 = c * WG_KP; a2 = 0; a3 = 0; b1 = a1; b2 = 0; b3 = 0; }
+          else { a1 = 0; a2 = (c % 5) * 2; a3 = (c / 5) * 4; b1 = dx; b2 = a2 + dy; b3 = a3; }
+#pragma unroll
+          for (int i = 0; i < WG_M / 32; ++i)
+            tma_load_4d(&tmA, &full_bar[stage], sa + i * WG_BOX_BYTES, mt * WG_M + i * 32, a1, a2, a3);
+#pragma unroll
+          for (int i = 0; i < WG_N / 32; ++i)
+            tma_load_4d(&tmB, &full_bar[stage], sb + i * WG_BOX_BYTES, nt * WG_N + i * 32, b1, b2, b3);
+        }
+        __syncwarp();
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_tf32(WG_M, WG_N, 1, 1);          // both operands MN-major
+    constexpr uint64_t dbase = umma_desc_base_sw128(WG_BOX_BYTES, 1024);   // LBO = next 32 channels, SBO = next 8 rows
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int mt, nt, tap, sp;
+      decode(tile, mt, nt, tap, sp);
+      const int c_begin = sp * p.chunks_per_split;
+      const int c_end = min(c_begin + p.chunks_per_split, p.n_chunks);
+      mbar_wait(&acc_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * WG_N;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
+          const uint64_t adesc = umma_desc(dbase, sa);
+          const uint64_t bdesc = umma_desc(dbase, sa + WG_A_BYTES);
+#pragma unroll
+          for (int g = 0; g < WG_KP / 8; ++g)   // 8 pixel rows = 1024 bytes (>>4 = 64) per K-step
+            umma_tf32(d_tmem, adesc + 64 * g, bdesc + 64 * g, idesc, (c > c_begin || g > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (c == c_end - 1) umma_commit(&acc_full[as]);
+        }
+        __syncwarp();
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int mt, nt, tap, sp;
+      decode(tile, mt, nt, tap, sp);
+      const int co = mt * WG_M + ew * 32 + lane;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * WG_N;
+#pragma unroll 1
+      for (int j0 = 0; j0 < WG_N; j0 += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(t_base + j0, v);
+        tmem_ld_wait();
+        if (co < p.cout) {
+          float* orow = p.out + (long long)co * p.out_co_stride + tap;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ci = nt * WG_N + j0 + j;
+            if (ci < p.cin) atomicAdd(orow + (long long)ci * p.out_ci_stride, __uint_as_float(v[j]));
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, WG_TMEM_COLS);
+}
+
+}  // namespace vnqa
+
+using namespace vnqa;
+
+// dw must be zero-initialised by the caller (partial tiles are accumulated atomically).
+// conv (flat = 0): dy [n_img][130][cout], x [n_img][130][cin], dw (cout, cin, taps) PyTorch layout.
+// flat = 1: dy [n_rows][cout], x [n_rows][cin], dw (cout, cin) row-major.
+extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32_t n_img, int32_t cout, int32_t cin,
+                               int32_t taps, int32_t flat, void* stream) {
+  VNQA_REQUIRE(dy && x && dw, "vnqa_conv_wgrad: null pointer");
+  VNQA_REQUIRE(taps == 1 || taps == 9, "vnqa_conv_wgrad: taps must be 1 or 9");
+  VNQA_REQUIRE(cout % 32 == 0 && cin % 32 == 0, "vnqa_conv_wgrad: channels must be multiples of 32 (%d, %d)", cout, cin);
+  VNQA_REQUIRE(!(flat && taps != 1), "vnqa_conv_wgrad: flat GEMM has one tap");
+  WParams wp{};
+  wp.taps = taps;
+  wp.m_tiles = (cout + WG_M - 1) / WG_M;
+  wp.n_tiles = (cin + WG_N - 1) / WG_N;
+  wp.flat = flat;
+  wp.cout = cout;
+  wp.cin = cin;
+  wp.n_chunks = flat ? (n_img + WG_KP - 1) / WG_KP : ((n_img + 3) / 4) * 5;
+  wp.out = dw;
+  wp.out_co_stride = (long long)cin * taps;
+  wp.out_ci_stride = taps;
+  const int sms = vnqa_sm_count();
+  if (sms <= 0) return -2;
+  // split-K: fill the machine with whole waves
+  const int base_tiles = wp.m_tiles * wp.n_tiles * taps;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 32 && s <= wp.n_chunks; ++s) {
+    const int tiles = base_tiles * s;
+    const int waves = (tiles + sms - 1) / sms;
+    double eff = (double)tiles / ((double)waves * sms);
+    if (wp.n_chunks / s < 8) eff *= 0.5;  // too little work per tile to amortise prologue/epilogue
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  wp.splits = best;
+  wp.chunks_per_split = (wp.n_chunks + best - 1) / best;
+
+  CUtensorMap tmA, tmB;
+  auto make = [&](CUtensorMap* m, const float* base, int C) -> int {
+    if (flat) {
+      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)n_img, 1, 1};
+      const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)C * 4 * n_img, (uint64_t)C * 4 * n_img};
+      const uint32_t box[4] = {32, WG_KP, 1, 1};
+      return make_tmap_f32(m, base, 4, dims, strides, box);
+    }
+    const uint64_t dims[4] = {(uint64_t)C, VNQA_IMG_W, VNQA_IMG_H, (uint64_t)n_img};
+    const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)C * 4 * VNQA_IMG_W, (uint64_t)C * 4 * VNQA_IMG_PIX};
+    const uint32_t box[4] = {32, VNQA_IMG_W, 2, 4};
+    return make_tmap_f32(m, base, 4, dims, strides, box);
+  };
+  if (make(&tmA, dy, cout) || make(&tmB, x, cin)) return -3;
+  const int total = base_tiles * wp.splits;
+  const int grid = total < sms ? total : sms;
+  VNQA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+  wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, as_stream(stream)>>>(tmA, tmB, wp);
+  VNQA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
