@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the FiLM video-QA hot path (BASELINE.json metric: video-QA clips/sec, FiLM-attn fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|eval] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic clips: FiLMAttnPretrainedStem with the eval.sh
+hyper-parameters (C_in 512, C 1024, 5 ResBlocks, hidden 128, 70 classes), 64 clips x 35 frames x 512 x 10 x 13 per GPU
+(config 4 = the same at 2/4/8 GPUs, weak scaling, one NCCL SUM all-reduce of the gradients
+per step overlapped with backward).  train step = forward + CrossEntropy(sum) + backward (+ all-reduce) +
+clip_grad_norm + Adam, exactly the reference's loop body (eval/q_and_v_eval.py:119-139).
+
+`value`   clips/s with the batch already resident in HBM (CUDA events, max over ranks).
+`e2e`     same metric through the public module API with HOST (pinned) inputs: every step copies that step's
+          v_input/q_input/lengths/labels host->device (prefetched on a copy stream) and reads the loss back.
+`roofline` tensor-core roofline of the dominant kernel (conv3x3 + FiLM epilogue, tcgen05 kind::tf32) timed per
+          launch with CUDA events inside the timed region; peak = measured bf16 dense TFLOP/s / 2 (tf32 runs at half
+          the bf16 rate) from MEASURED_PEAKS.json.
+`cpu_baseline` the CPU oracle (port of the reference, oracle/film_oracle.py) on the host cores, bounded sample.
+--impl reference: only the CPU leg, as its own JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(c_in=512, C=1024, nb=5, hidden=128, at_hidden=128, embed=128, vocab=134, classes=70, T=35, Lq=56)
+FWD_GFLOP_PER_CLIP = 521.85
+TRAIN_GFLOP_PER_CLIP = 1522.61
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", choices=["train", "eval"], default="train")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU")
+    ap.add_argument("--ragged", action="store_true", help="ragged v_lens (secondary config) instead of all 35")
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- CPU leg
+def cpu_leg(workload, clips, iters=1, warm=0):
+    """Time the CPU oracle (port of the reference forward/backward) on all host cores, bounded sample."""
+    import torch
+    from oracle import film_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = O.init_params("attn", c_in=CFG["c_in"], C=CFG["C"], nb=CFG["nb"], hidden=CFG["hidden"],
+                      at_hidden=CFG["at_hidden"], embed=CFG["embed"], vocab=CFG["vocab"], classes=CFG["classes"],
+                      T=CFG["T"], seed=1)
+    v, q, v_lens, q_lens, labels = O.synthetic_batch(clips, c_in=CFG["c_in"], T=CFG["T"], Lq=CFG["Lq"],
+                                                     vocab=CFG["vocab"], classes=CFG["classes"], seed=0)
+    times = []
+    for i in range(warm + iters):
+        bn = O.new_bn_state(CFG["C"])
+        st = O.new_film_state(clips, CFG["hidden"])
+        t0 = time.perf_counter()
+        if workload == "train":
+            O.loss_and_grads("attn", p, bn, st, v, q, v_lens, q_lens, labels, training=True)
+        else:
+            with torch.no_grad():
+                O.film_attn_forward(p, bn, st, v, q, v_lens, q_lens, training=False)
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": clips / sec, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{clips} full-length clips (35 frames), {workload} step, {iters} timed run(s), "
+                      f"torch CPU fp32 with {cores} threads", "sec_per_step": sec}
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+                if self._stop.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for n, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- GPU leg
+def gpu_leg(args):
+    import torch
+    import torch.distributed as dist
+    from oracle.film_oracle import synthetic_batch          # input generator only (numpy RNG); not timed
+    from videonavqa_b200 import dp, ops
+    from videonavqa_b200.models import FiLMAttnPretrainedStem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(1)
+    model = FiLMAttnPretrainedStem(batch_size=B, q_embedding_size=CFG["embed"], nb_classes=CFG["classes"],
+                                   num_input_channels=CFG["c_in"], num_res_block_channels=CFG["C"],
+                                   num_res_blocks=CFG["nb"], hidden_size=CFG["hidden"], at_hidden_size=CFG["at_hidden"],
+                                   max_num_frames=CFG["T"], vocab_size=CFG["vocab"]).to(dev)
+    reducer = None
+    if world > 1:
+        dp.broadcast_module(model)
+        reducer = dp.GradAllReducer(model)
+    train = args.workload == "train"
+    model.train(train)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4) if train else None        # eval.sh:16
+
+    # synthetic clips, a different shard per rank; kept in pinned host memory for the e2e leg
+    v, q, v_lens, q_lens, labels = synthetic_batch(B, c_in=CFG["c_in"], T=CFG["T"], Lq=CFG["Lq"], vocab=CFG["vocab"],
+                                                   classes=CFG["classes"], seed=rank, ragged=args.ragged)
+    host = [t.pin_memory() for t in (v, q, v_lens, q_lens, labels)]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    n_frames_total = int(v_lens.sum())
+
+    def step(dv, dq, dvl, dql, dlab):
+        model.init_hidden()                                                        # q_and_v_eval.py:119-120
+        if not train:
+            with torch.no_grad():
+                return model(dv, dq, dvl, dql)
+        out = model(dv, dq, dvl, dql)
+        loss = torch.nn.functional.cross_entropy(out, dlab, reduction="sum")       # eval.sh:15
+        loss.backward()                                                            # all-reduce overlapped inside
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                    # q_and_v_eval.py:137
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    dev_in = [t.to(dev) for t in host]
+    for _ in range(args.warmup):
+        step(*dev_in)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE = []
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(*dev_in)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (ops.LAUNCHES - launches0) // args.steps
+    prof, ops.PROFILE = ops.PROFILE, None
+    if rank == 0:
+        sampler.stop()
+    # per-kernel-class durations from the in-region events
+    klass = {}
+    for tag, flops, a, b in prof:
+        d = klass.setdefault(tag, [0.0, 0, flops])
+        d[0] += a.elapsed_time(b); d[1] += 1
+
+    # ---------------- end-to-end timing: host inputs every step, prefetched on a copy stream, loss read back
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            t = [x.to(dev, non_blocking=True) for x in host]
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        return t, ev
+
+    for _ in range(2):
+        t, ev = fetch(); torch.cuda.current_stream().wait_event(ev); r = step(*t); float(r.sum())
+    barrier()
+    d2h = 4 if train else B * CFG["classes"] * 4
+    t_wall0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    nxt = fetch()
+    for i in range(args.steps):
+        t, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        for x in t:
+            x.record_stream(torch.cuda.current_stream())
+        if i + 1 < args.steps:
+            nxt = fetch()                      # overlaps with this step's compute
+        r = step(*t)
+        _ = r.item() if train else r.cpu()     # device->host read of the step result
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1) / args.steps
+    del t_wall0
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)"
+                if peaks else "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)")
+    tf32_peak = bf16_peak / 2.0
+    dom_tag = f"conv_gemm.9tap.epi3.k{CFG['C']}.n{CFG['C']}"            # conv3x3 + FiLM epilogue (forward)
+    kernels = {}
+    for tag, (tot, n, flops) in sorted(klass.items(), key=lambda kv: -kv[1][0]):
+        kernels[tag] = {"launches_per_step": n // args.steps, "ms_per_launch": round(tot / n, 4),
+                        "tflops": round(flops / (tot / n) * 1e-9, 1), "share_of_step": round(tot / args.steps / ms, 4)}
+    roof = None
+    if dom_tag in kernels:
+        k = kernels[dom_tag]
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_tag)
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<EPI_FILM> (conv3x3 1024->1024 + FiLM/ReLU/residual)",
+                "achieved": k["tflops"], "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                "frac": round(k["tflops"] / tf32_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "flops_per_launch": klass[dom_tag][2], "ms_per_launch": k["ms_per_launch"]}
+    clips = B * world
+    gflop = TRAIN_GFLOP_PER_CLIP if train else FWD_GFLOP_PER_CLIP
+    scale = n_frames_total / (B * CFG["T"])
+    out = {
+        "metric": "video-QA clips/sec (FiLM-attn fwd+bwd)" if train else "video-QA clips/sec (FiLM-attn eval forward)",
+        "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32 operands, fp32 accumulate/storage", "data": "synthetic",
+        "config": {"workload": f"film_attn_pt {args.workload} step, eval.sh hyper-parameters (C_in 512, C 1024, 5 blocks,"
+                               f" hidden 128, 70 classes), {B} clips/GPU x 35 frames x 512x10x13"
+                               + (", ragged v_lens" if args.ragged else ", all clips 35 frames"),
+                   "global_batch": clips, "frames_per_clip": CFG["T"], "parallelism": f"dp{world}",
+                   "step": "fwd+CE(sum)+bwd" + ("+allreduce(sum)" if world > 1 else "") + "+clip_grad_norm+Adam" if train
+                   else "eval forward", "l2": "inputs larger than L2 (v_input 596 MB, activations 1.19 GB each)",
+                   "frame_images_per_step": n_frames_total * world},
+        "model_tflops": round(clips * gflop * scale / ms, 1),
+        "e2e": {"value": round(clips / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3)},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": roof,
+        "kernels": kernels,
+    }
+    if reducer is not None:
+        out["allreduce_bytes_per_step"] = getattr(reducer, "last_bytes", None)
+    if world > 1:
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        iters = max(1, min(args.steps, 3))
+        cb = cpu_leg(args.workload, args.cpu_clips, iters=iters, warm=min(args.warmup, 1))
+        line = {"impl": "reference",
+                "metric": "video-QA clips/sec (FiLM-attn fwd+bwd)" if args.workload == "train"
+                else "video-QA clips/sec (FiLM-attn eval forward)",
+                "value": round(cb["value"], 4), "unit": "clips/s", "n_gpus": args.gpus, "steps": iters,
+                "warmup": min(args.warmup, 1), "ms_per_step": round(cb["sec_per_step"] * 1e3, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": f"film_attn_pt {args.workload} step, eval.sh hyper-parameters; CPU oracle "
+                                       f"(port of the reference) on a bounded sample of {args.cpu_clips} clips x 35 frames"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": round(cb["value"], 4), "unit": "clips/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    out = gpu_leg(args)
+    if out is None:
+        return
+    if args.gpus == 1 and not args.no_cpu:
+        cb = cpu_leg(args.workload, args.cpu_clips)
+        out["cpu_baseline"] = {k: (round(cb[k], 4) if k == "value" else cb[k])
+                               for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

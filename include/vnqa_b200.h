@@ -138,8 +138,9 @@ int vnqa_film_backward(const float* dout, const float* z, const float* film, con
 /* out[dst_row[r]][n] = bias[n] + sum_s partial[s][r][n] */
 int vnqa_splitk_reduce(const float* partial, int32_t splits, int32_t rows, int32_t N, const float* bias,
                        const int32_t* dst_row, float* out, void* stream);
-/* out[r][:] = src[src_row[r]][:] */
-int vnqa_gather_rows(const float* src, const int32_t* src_row, int32_t rows, int32_t N, float* out, void* stream);
+/* out[r][:] = src[src_row[r]][:]  (round_tf32 != 0 when the result feeds an MMA) */
+int vnqa_gather_rows(const float* src, const int32_t* src_row, int32_t rows, int32_t N, float* out,
+                     int32_t round_tf32, void* stream);
 
 /* ---- global temporal max pooling (models/film_global_pooling_pt_stem.py:230-235) */
 int vnqa_gp_maxpool(const float* y, const int32_t* img_of, int32_t B, int32_t T, int32_t tail, float* pooled,

@@ -24,6 +24,38 @@ import torch.nn.functional as F
 
 NEG_MASK = float(-(1 << 31))  # models/film_attn_pt_stem.py:251
 
+# --------------------------------------------------------------------------------------
+# Optional emulation of the product's operand rounding.  The CUDA path feeds its tensor-core MMAs with
+# tf32 operands (10-bit mantissa, round-to-nearest applied once by the producer of each tensor: packed
+# weights, the NHWC input, the BatchNorm output, every ResBlock activation).  With ``emulate_tf32()`` active the
+# oracle rounds at exactly those points (straight-through in backward), so that ReLU masks agree and a gradient
+# comparison measures implementation errors rather than mask flips.  Default (off) = the plain fp32 reference.
+# --------------------------------------------------------------------------------------
+_EMULATE_TF32 = False
+
+
+class emulate_tf32:
+    def __enter__(self):
+        global _EMULATE_TF32
+        self._old, _EMULATE_TF32 = _EMULATE_TF32, True
+
+    def __exit__(self, *a):
+        global _EMULATE_TF32
+        _EMULATE_TF32 = self._old
+
+
+def tf32_round(t):
+    """cvt.rna.tf32.f32: round to nearest (ties away) to a 10-bit mantissa."""
+    i = t.detach().contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    return r
+
+
+def _q(t):
+    if not _EMULATE_TF32 or t.dtype != torch.float32:
+        return t
+    return t + (tf32_round(t) - t).detach()
+
 
 # --------------------------------------------------------------------------------------
 # Question encoder: embedding + packed LSTM with state carried across frames
@@ -93,21 +125,21 @@ def conv_init_bn(p, bn_state, x, training):
     """bn_init(relu(conv_init(x))) (models/film_attn_pt_stem.py:211): conv3x3 pad 1, ReLU, THEN
     BatchNorm2d (eps 1e-5, momentum 0.1).  ``bn_state`` = dict(running_mean, running_var,
     num_batches_tracked) updated in place in training mode (quirk Q6)."""
-    y = F.relu(F.conv2d(x, p["conv_init.weight"], p["conv_init.bias"], padding=1))
+    y = F.relu(F.conv2d(_q(x), _q(p["conv_init.weight"]), p["conv_init.bias"], padding=1))
     out = F.batch_norm(y, bn_state["running_mean"], bn_state["running_var"],
                        p["bn_init.weight"], p["bn_init.bias"],
                        training=training, momentum=0.1, eps=1e-5)
     if training:
         bn_state["num_batches_tracked"] += 1
-    return out
+    return _q(out)
 
 
 def film_res_block(p, k, x, alphas, betas):
     """One FiLM ResBlock (models/film_attn_pt_stem.py:217-241):
     res = relu(conv1x1_k(x)); z = conv3x3_k(res); out = relu(alpha*z + beta) + res."""
-    res = F.relu(F.conv2d(x, p[f"conv1x1_layers.{k}.weight"], p[f"conv1x1_layers.{k}.bias"]))
-    z = F.conv2d(res, p[f"film_pipeline.{k}.weight"], p[f"film_pipeline.{k}.bias"], padding=1)
-    return F.relu(alphas[:, :, None, None] * z + betas[:, :, None, None]) + res
+    res = _q(F.relu(F.conv2d(x, _q(p[f"conv1x1_layers.{k}.weight"]), p[f"conv1x1_layers.{k}.bias"])))
+    z = F.conv2d(res, _q(p[f"film_pipeline.{k}.weight"]), p[f"film_pipeline.{k}.bias"], padding=1)
+    return _q(F.relu(alphas[:, :, None, None] * z + betas[:, :, None, None]) + res)
 
 
 def film_stack(p, x, film, num_blocks):
@@ -145,7 +177,7 @@ def film_attn_forward(p, bn_state, film_state, v_input, q_input, v_lens, q_lens,
         x = conv_init_bn(p, bn_state, v_input[:ct, :, :, :, i], training)   # :210-211
         film, film_state = film_values_lstm(p, "film_layer.", q_input, q_lens, film_state)  # :213
         x = film_stack(p, x, film[:ct], nb)                    # :215-241
-        f = F.linear(x.reshape(ct, -1), p["fc_embed_attn.weight"], p["fc_embed_attn.bias"])  # :244
+        f = F.linear(x.reshape(ct, -1), _q(p["fc_embed_attn.weight"]), p["fc_embed_attn.bias"])  # :244
         feats[:ct, i] = f
         masks[ct:, i, 0] = NEG_MASK                            # :251 (processed frames only, Q5)
     # frame scores on valid (b, t) only, zero elsewhere (:268-281)
@@ -171,7 +203,7 @@ def film_attn_forward(p, bn_state, film_state, v_input, q_input, v_lens, q_lens,
 # --------------------------------------------------------------------------------------
 def gp_tail(p, x):
     """relu(c1x1_tail(x)) flattened channel-major (models/film_global_pooling_pt_stem.py:228-232)."""
-    y = F.relu(F.conv2d(x, p["c1x1_tail.weight"], p["c1x1_tail.bias"]))
+    y = F.relu(F.conv2d(x, _q(p["c1x1_tail.weight"]), p["c1x1_tail.bias"]))
     return y.reshape(y.shape[0], -1)
 
 
@@ -218,8 +250,8 @@ def tmh_forward(p, bn_state, film_state, v_input, q_input, v_lens, q_lens, train
         rnn = states[:ct]
         start = 0
         for k in range(nb):
-            res = F.relu(F.conv2d(x, p[f"conv1x1_layers.{k}.weight"], p[f"conv1x1_layers.{k}.bias"]))
-            z = F.conv2d(res, p[f"film_pipeline.{k}.weight"], p[f"film_pipeline.{k}.bias"], padding=1)
+            res = _q(F.relu(F.conv2d(x, _q(p[f"conv1x1_layers.{k}.weight"]), p[f"conv1x1_layers.{k}.bias"])))
+            z = F.conv2d(res, _q(p[f"film_pipeline.{k}.weight"]), p[f"film_pipeline.{k}.bias"], padding=1)
             e = hctx * rnn                                      # :170
             coefs = torch.softmax(F.linear(e, p["fc_hidden_attn.weight"], p["fc_hidden_attn.bias"]), dim=1)
             hvec = torch.bmm(coefs.view(ct, 1, W), e).view(ct, H)   # :175-176
@@ -228,7 +260,7 @@ def tmh_forward(p, bn_state, film_state, v_input, q_input, v_lens, q_lens, train
             film = F.layer_norm(cond, (cond.shape[1],), p["decoder_norm.weight"], p["decoder_norm.bias"], 1e-5)
             a, b = film[:, start:start + C], film[:, start + C:start + 2 * C]
             start += 2 * C
-            x = F.relu(a[:, :, None, None] * z + b[:, :, None, None]) + res
+            x = _q(F.relu(a[:, :, None, None] * z + b[:, :, None, None]) + res)
         y = gp_tail(p, x)
         per_frame.append(F.pad(y, (0, 0, 0, B - ct)))
     pooled = torch.stack(per_frame, dim=0).max(dim=0)[0]

@@ -254,7 +254,7 @@ static int run_case(const Case& c) {
                        c.epi == VNQA_EPI_DGRAD_RES;
   // operands are pre-rounded (rna), so the rna reference must match to accumulation-order noise; rounded outputs
   // may differ by one tf32 ulp (2^-10 relative) where the fp32 sums differ in the last bits
-  if (!(n0 < 3e-3) || !(n1 < (rounded ? 1.1e-3 : 2e-5))) fail = 1;
+  if (!(n0 < 3e-3) || !(n1 < (rounded ? 1.1e-3 : 1e-4))) fail = 1;
   if (c.epi == VNQA_EPI_BIAS_RELU_STATS && c.samples == 0) {
     double es = 0, ms = 0;
     for (size_t i = 0; i < ssum.size(); ++i) {

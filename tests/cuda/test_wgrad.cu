@@ -61,8 +61,11 @@ static int run_case(const Case& c) {
   fill_kernel<<<148 * 8, 256>>>(dy, rows * c.cout, 17u, 1.0f);
   fill_kernel<<<148 * 8, 256>>>(x, rows * c.cin, 99u, 1.0f);
   CK(cudaMemset(dw, 0, wn * 4));
+  CK(cudaDeviceSynchronize());
+  fprintf(stderr, "[%s] inputs ready\n", c.name);
   CKV(vnqa_conv_wgrad(dy, x, dw, c.n_img, c.cout, c.cin, c.taps, c.flat, nullptr));
   CK(cudaDeviceSynchronize());
+  fprintf(stderr, "[%s] wgrad done\n", c.name);
   const int ns = 512;
   std::vector<int> hs(3 * ns);
   uint32_t seed = 777;
@@ -80,6 +83,13 @@ static int run_case(const Case& c) {
   CK(cudaMalloc(&dref, ns * 8));
   ref_kernel<<<ns, 256>>>(dy, x, dref, ds, ns, c.cout, c.cin, c.taps, c.n_img, c.flat);
   CK(cudaDeviceSynchronize());
+  if (getenv("VNQA_TEST_VERBOSE")) {
+    std::vector<float> h0(wn);
+    CK(cudaMemcpy(h0.data(), dw, wn * 4, cudaMemcpyDeviceToHost));
+    size_t nz = 0; double mxv = 0;
+    for (size_t i = 0; i < wn; ++i) { if (h0[i] != 0.f) ++nz; mxv = fmax(mxv, fabs(h0[i])); }
+    printf("   dw: %zu of %zu non-zero, max |dw| %.4f\n", nz, wn, mxv);
+  }
   std::vector<double> href(ns);
   std::vector<float> hw(wn);
   CK(cudaMemcpy(href.data(), dref, ns * 8, cudaMemcpyDeviceToHost));
@@ -87,6 +97,7 @@ static int run_case(const Case& c) {
   double err = 0, mx = 0;
   for (int i = 0; i < ns; ++i) {
     const double got = hw[((size_t)hs[3 * i] * c.cin + hs[3 * i + 1]) * c.taps + hs[3 * i + 2]];
+    if (i < 4 && getenv("VNQA_TEST_VERBOSE")) printf("   sample co %d ci %d tap %d: got %.6f ref %.6f\n", hs[3*i], hs[3*i+1], hs[3*i+2], got, href[i]);
     err = fmax(err, fabs(got - href[i]));
     mx = fmax(mx, fabs(href[i]));
   }

@@ -1,0 +1,96 @@
+"""ctypes binding of libvnqa_b200.so (C ABI in include/vnqa_b200.h).
+
+There is no fallback: if the shared library has not been built (``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C videonavqa_b200/csrc``) importing a symbol raises, and every compute entry point
+needs a CUDA sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvnqa_b200.so")
+
+
+class VnqaError(RuntimeError):
+    pass
+
+
+class ConvArgs(ctypes.Structure):
+    """Mirror of vnqa_conv_args (include/vnqa_b200.h)."""
+    _fields_ = [
+        ("w_packed", c_void_p), ("x", c_void_p),
+        ("taps", c_int32), ("cin", c_int32), ("cout", c_int32), ("rows_pad", c_int32), ("n_img", c_int32),
+        ("flat", c_int32), ("x_ld", c_int32), ("splits", c_int32), ("epi", c_int32), ("no_round", c_int32),
+        ("out", c_void_p), ("bias", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+        ("img_frame", c_void_p), ("stat_sum", c_void_p), ("stat_sq", c_void_p),
+        ("film", c_void_p), ("film_row", c_void_p), ("film_ld", c_int32), ("alpha_off", c_int32),
+        ("res", c_void_p), ("z_out", c_void_p), ("add", c_void_p), ("dbias", c_void_p),
+    ]
+
+
+EPI_BIAS_RELU, EPI_BIAS_RELU_AFFINE, EPI_BIAS_RELU_STATS, EPI_FILM, EPI_PARTIAL, EPI_DGRAD_RES = 0, 1, 2, 3, 4, 5
+EPI_PLAIN = 7
+
+P, I32, I64, F32 = c_void_p, c_int32, c_int64, c_float
+
+# name -> argtypes (every function returns int unless listed in _RESTYPES)
+SIGNATURES = {
+    "vnqa_abi_version": [],
+    "vnqa_last_error": [],
+    "vnqa_device_check": [],
+    "vnqa_sm_count": [],
+    "vnqa_frames_to_nhwc": [P, P, P, I32, I32, I32, P],
+    "vnqa_pack_conv_weight": [P, P, I32, I32, I32, I32, I32, P],
+    "vnqa_permute_fc_weight": [P, P, I32, I32, I32, I32, P],
+    "vnqa_conv_gemm": [POINTER(ConvArgs), P],
+    "vnqa_conv_wgrad": [P, P, P, I32, I32, I32, I32, I32, P],
+    "vnqa_sgemm": [P, P, P, P, I32, I32, I32, I64, I64, I64, I64, I64, I32, I32, I32, P],
+    "vnqa_colsum": [P, I32, I32, I64, P, I32, P],
+    "vnqa_bn_finalize_train": [P, P, P, I32, I32, P, P, P, P, F32, F32, P, P, P, P, P],
+    "vnqa_bn_eval_affine": [P, P, P, P, F32, I32, P, P, P],
+    "vnqa_bn_apply": [P, P, P, P, P, I32, I32, P],
+    "vnqa_bn_backward": [P, P, P, P, I32, P, P, P, I32, I32, P, P, P, P, P, P, P],
+    "vnqa_film_backward": [P, P, P, P, I32, I32, I32, I32, P, P, P, P],
+    "vnqa_splitk_reduce": [P, I32, I32, I32, P, P, P, P],
+    "vnqa_gather_rows": [P, P, I32, I32, P, I32, P],
+    "vnqa_gp_maxpool": [P, P, I32, I32, I32, P, P, P],
+    "vnqa_gp_maxpool_backward": [P, P, P, I32, I32, P, P],
+    "vnqa_embed_gates": [P, P, P, P, P, P, I32, I32, I32, I32, P, P],
+    "vnqa_lstm_chain_forward": [P, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P],
+    "vnqa_lstm_chain_backward": [P, P, P, P, P, P, I32, I32, I32, I32, P, P, P],
+    "vnqa_embed_backward": [P, P, P, I32, I32, I32, P, P],
+    "vnqa_embed_gather": [P, P, P, I32, I32, I32, P, P],
+    "vnqa_attn_tail_forward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
+    "vnqa_attn_tail_backward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
+}
+_RESTYPES = {"vnqa_last_error": c_char_p}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library once; fail loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VnqaError(
+                f"{LIB_PATH} is missing: build it with `make -C videonavqa_b200/csrc` "
+                "(or __graft_entry__.build()); videonavqa_b200 has no CPU or PyTorch fallback")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the library does not export a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int32)
+        if handle.vnqa_abi_version() != 1:
+            raise VnqaError("libvnqa_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vnqa_last_error()
+        raise VnqaError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")

@@ -29,7 +29,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+                  const uint32_t* box, bool atom32) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -46,7 +46,9 @@ int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* di
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,

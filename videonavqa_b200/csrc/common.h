@@ -34,10 +34,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 
-// fp32 tensor map with 128-byte swizzle and zero out-of-bounds fill. dims/strides innermost first;
+// fp32 tensor map with 128-byte swizzle (16-byte atoms, or 32-byte atoms for MN-major MMA operands when atom32)
+// and zero out-of-bounds fill. dims/strides innermost first;
 // strides in bytes for dims 1..rank-1.
 int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box);
+                  const uint32_t* box, bool atom32 = false);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

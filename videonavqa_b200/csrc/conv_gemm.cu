@@ -125,7 +125,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int dy = 0, dx = 0;
         if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           if (lane == 0) {
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
@@ -147,11 +147,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&acc_empty[as], aphase ^ 1);
+      mbar_wait(&acc_empty[as], aphase ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * ACC_COLS;
       for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -196,7 +196,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int st_frame = -1;
       float db_acc = 0.f;                // DGRAD_RES: per-channel sum
 
-      mbar_wait(&acc_full[as], aphase);
+      mbar_wait(&acc_full[as], aphase, 4);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * ACC_COLS;
 

@@ -2,6 +2,7 @@
 // No CUTLASS dependency; bit layouts follow the PTX ISA "tcgen05" matrix/instruction descriptor tables.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -37,18 +38,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// Blocking wait with a watchdog: a pipeline bug traps (reported as a CUDA error with the barrier tag) instead of
+// hanging the GPU.  try_wait suspends the thread for a hardware time slice, so the spin count stays small.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins == (1u << 21)) {
+      printf("vnqa: mbarrier wait timed out (block %d thread %d tag %d parity %u)\n", blockIdx.x, threadIdx.x, tag,
+             parity);
+      __trap();
+    }
+  }
 }
 
 // ---------------------------------------------------------------- TMA
@@ -144,6 +157,13 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
 __host__ __device__ constexpr uint64_t umma_desc_base_sw128(uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);
+}
+// MN-major fp32/tf32 operands must use the "128B swizzle with 32B atoms" layout (type 1): 32-byte chunks of a
+// 128-byte row are XORed with (row % 4); K rows come in groups of 4 (SBO = 512 B when rows are dense), the next
+// 32 MN elements are LBO bytes away.  The matching TMA mode is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__host__ __device__ constexpr uint64_t umma_desc_base_sw128_32b(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(sbo_bytes >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(1) << 61);
 }
 __device__ __forceinline__ uint64_t umma_desc(uint64_t base, uint32_t smem_addr) {
   return base | uint64_t((smem_addr >> 4) & 0x3FFF);

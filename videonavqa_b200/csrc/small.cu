@@ -303,12 +303,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ src_row, long long rows, int N,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, int round_tf32) {
   const long long total = rows * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / N;
-    out[i] = __ldg(src + (long long)src_row[r] * N + (i % N));
+    const float v = __ldg(src + (long long)src_row[r] * N + (i % N));
+    out[i] = round_tf32 ? tf32_round(v) : v;
   }
 }
 
@@ -325,10 +326,10 @@ extern "C" int vnqa_colsum(const float* x, int32_t rows, int32_t n, int64_t ld, 
 }
 
 extern "C" int vnqa_gather_rows(const float* src, const int32_t* src_row, int32_t rows, int32_t N, float* out,
-                                void* stream) {
+                                int32_t round_tf32, void* stream) {
   const long long total = (long long)rows * N;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  gather_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, src_row, rows, N, out);
+  gather_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, src_row, rows, N, out, round_tf32);
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

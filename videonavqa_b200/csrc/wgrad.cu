@@ -5,11 +5,14 @@
 //
 // The reduction runs over PIXELS, and both operands are stored pixel-major ([row][channel], channel contiguous),
 // i.e. "MN-major" for the MMA: no transposed copies are made - the UMMA descriptors are built MN-major
-// (instruction-descriptor bits 15/16) over 128-byte-swizzled TMA boxes {32 channels x 104 pixel rows}
+// (instruction-descriptor bits 15/16, smem layout "128B swizzle / 32B atoms", the only one tf32 accepts
+// MN-major) over TMA boxes {32 channels x 104 pixel rows}
 // (104 = 4 images x 2 image rows x 13 = 13 MMA K-steps of 8).  Tap shifts and the zero halo are again TMA box
 // coordinates / out-of-bounds fill.  Tile = 128 (co) x 128 (ci) fp32 accumulators in TMEM, 2 smem stages of
 // 104 KB, split-K over pixel chunks to fill 148 SMs; partial tiles are reduced with fp32 red.global.add into the
 // zero-initialised gradient, written directly in PyTorch (Cout, Cin, kh, kw) layout.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -27,7 +30,7 @@ constexpr int WG_THREADS = 256;
 constexpr int WG_TMEM_COLS = 256;                // 2 accumulator stages x 128 columns
 
 struct WParams {
-  int taps, m_tiles, n_tiles, splits, n_chunks, chunks_per_split, flat;
+  int taps, m_tiles, n_tiles, splits, n_chunks, chunks_per_split, flat, debug;
   int cout, cin;          // real sizes (tiles beyond are skipped on store)
   long long out_co_stride, out_ci_stride;  // element strides of the output for (co, ci); tap stride is 1
   float* out;
@@ -58,6 +61,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.debug == 3 && blockIdx.x == 0 && (threadIdx.x & 31) == 0)
+    printf("wgrad dbg: warp %d past setup, tmem_base %u total_tiles %d chunks %d\n", warp, tmem_base, total_tiles, p.n_chunks);
 
   // tile -> (mt, nt, tap, split); mt fastest so that concurrently running CTAs share the X (B) slab in L2
   auto decode = [&](int tile, int& mt, int& nt, int& tap, int& sp) {
@@ -76,7 +81,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int c_begin = sp * p.chunks_per_split;
       const int c_end = min(c_begin + p.chunks_per_split, p.n_chunks);
       for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
         if (lane == 0) {
           uint8_t* sa = smem + stage * WG_STAGE_BYTES;
           uint8_t* sb = sa + WG_A_BYTES;
@@ -92,31 +97,35 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_4d(&tmB, &full_bar[stage], sb + i * WG_BOX_BYTES, nt * WG_N + i * 32, b1, b2, b3);
         }
         __syncwarp();
+        if (p.debug == 3 && blockIdx.x == 0 && lane == 0) printf("wgrad dbg: producer issued chunk %d stage %d\n", c, stage);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_tf32(WG_M, WG_N, 1, 1);          // both operands MN-major
-    constexpr uint64_t dbase = umma_desc_base_sw128(WG_BOX_BYTES, 1024);   // LBO = next 32 channels, SBO = next 8 rows
+    // both operands MN-major (debug 10..13 override the two major bits for bring-up experiments)
+    const uint32_t idesc = p.debug >= 10 ? umma_idesc_tf32(WG_M, WG_N, (p.debug - 10) & 1, ((p.debug - 10) >> 1) & 1)
+                                         : umma_idesc_tf32(WG_M, WG_N, 1, 1);
+    constexpr uint64_t dbase = umma_desc_base_sw128_32b(WG_BOX_BYTES, 512);  // LBO = next 32 channels, SBO = next 4 rows
     int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int mt, nt, tap, sp;
       decode(tile, mt, nt, tap, sp);
       const int c_begin = sp * p.chunks_per_split;
       const int c_end = min(c_begin + p.chunks_per_split, p.n_chunks);
-      mbar_wait(&acc_empty[as], aphase ^ 1);
+      mbar_wait(&acc_empty[as], aphase ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * WG_N;
       for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
+        if (p.debug == 3 && blockIdx.x == 0 && lane == 0) printf("wgrad dbg: mma got chunk %d stage %d\n", c, stage);
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
           const uint64_t adesc = umma_desc(dbase, sa);
           const uint64_t bdesc = umma_desc(dbase, sa + WG_A_BYTES);
 #pragma unroll
           for (int g = 0; g < WG_KP / 8; ++g)   // 8 pixel rows = 1024 bytes (>>4 = 64) per K-step
-            umma_tf32(d_tmem, adesc + 64 * g, bdesc + 64 * g, idesc, (c > c_begin || g > 0) ? 1u : 0u);
+            if (p.debug != 1) umma_tf32(d_tmem, adesc + 64 * g, bdesc + 64 * g, idesc, (c > c_begin || g > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (c == c_end - 1) umma_commit(&acc_full[as]);
         }
@@ -133,7 +142,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int mt, nt, tap, sp;
       decode(tile, mt, nt, tap, sp);
       const int co = mt * WG_M + ew * 32 + lane;
-      mbar_wait(&acc_full[as], aphase);
+      mbar_wait(&acc_full[as], aphase, 4);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * WG_N;
 #pragma unroll 1
@@ -181,6 +190,7 @@ extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32
   wp.m_tiles = (cout + WG_M - 1) / WG_M;
   wp.n_tiles = (cin + WG_N - 1) / WG_N;
   wp.flat = flat;
+  { const char* e = getenv("VNQA_WGRAD_DEBUG"); wp.debug = e ? atoi(e) : 0; }
   wp.cout = cout;
   wp.cin = cin;
   wp.n_chunks = flat ? (n_img + WG_KP - 1) / WG_KP : ((n_img + 3) / 4) * 5;
@@ -192,13 +202,16 @@ extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32
   // split-K: fill the machine with whole waves
   const int base_tiles = wp.m_tiles * wp.n_tiles * taps;
   int best = 1;
-  double best_eff = 0.0;
+  double best_eff = -1.0;
   for (int s = 1; s <= 32 && s <= wp.n_chunks; ++s) {
+    const int cps = (wp.n_chunks + s - 1) / s;
+    const int real = (wp.n_chunks + cps - 1) / cps;   // splits that actually own chunks
+    if (real != s) continue;
     const int tiles = base_tiles * s;
     const int waves = (tiles + sms - 1) / sms;
     double eff = (double)tiles / ((double)waves * sms);
-    if (wp.n_chunks / s < 8) eff *= 0.5;  // too little work per tile to amortise prologue/epilogue
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    if (cps < 8 && s > 1) eff *= 0.5;  // too little work per tile to amortise prologue/epilogue
+    if (eff > best_eff * 1.03) { best_eff = eff; best = s; }
   }
   wp.splits = best;
   wp.chunks_per_split = (wp.n_chunks + best - 1) / best;
@@ -209,12 +222,12 @@ extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32
       const uint64_t dims[4] = {(uint64_t)C, (uint64_t)n_img, 1, 1};
       const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)C * 4 * n_img, (uint64_t)C * 4 * n_img};
       const uint32_t box[4] = {32, WG_KP, 1, 1};
-      return make_tmap_f32(m, base, 4, dims, strides, box);
+      return make_tmap_f32(m, base, 4, dims, strides, box, true);
     }
     const uint64_t dims[4] = {(uint64_t)C, VNQA_IMG_W, VNQA_IMG_H, (uint64_t)n_img};
     const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)C * 4 * VNQA_IMG_W, (uint64_t)C * 4 * VNQA_IMG_PIX};
     const uint32_t box[4] = {32, VNQA_IMG_W, 2, 4};
-    return make_tmap_f32(m, base, 4, dims, strides, box);
+    return make_tmap_f32(m, base, 4, dims, strides, box, true);
   };
   if (make(&tmA, dy, cout) || make(&tmB, x, cin)) return -3;
   const int total = base_tiles * wp.splits;

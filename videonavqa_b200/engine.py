@@ -1,0 +1,390 @@
+"""Forward / backward orchestration of the FiLM hot path on top of the C-ABI kernels.
+
+The reference runs a Python loop over the 35 frames with ~25 launches each
+(models/film_attn_pt_stem.py:201-251).  Here every layer runs ONCE over all n_img = sum(v_lens) frame images
+("frame-batched"): frames only couple through the BatchNorm running statistics (sequential EMA, reproduced by
+vnqa_bn_finalize_train) and through the video-independent question-LSTM chain (vnqa_lstm_chain_forward), so
+this is exactly the same arithmetic per image.
+
+Everything here is host-side plumbing (buffer allocation through PyTorch's caching allocator, launch order);
+no tensor arithmetic is done with torch ops on the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import (EPI_BIAS_RELU, EPI_BIAS_RELU_AFFINE, EPI_BIAS_RELU_STATS, EPI_DGRAD_RES, EPI_FILM, EPI_PARTIAL,
+                   EPI_PLAIN)
+
+IMG_PIX = 130
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class Plan:
+    """Ragged-batch bookkeeping (models/film_attn_pt_stem.py:190-210, 245-251) computed once per forward on the
+    host from v_lens (ONE device->host read instead of the reference's >= 35)."""
+
+    def __init__(self, v_lens_host, B, T, device):
+        v = np.asarray(v_lens_host, dtype=np.int64)
+        if v.shape != (B,):
+            raise ValueError(f"v_lens must have shape ({B},), got {v.shape}")
+        if (np.diff(v) > 0).any():
+            raise ValueError("clips must be sorted by descending length (models/film_attn_pt_stem.py:184-186)")
+        if v.min() < 1 or v.max() > T:
+            raise ValueError(f"v_lens must lie in [1, {T}]")
+        self.B, self.T = B, T
+        self.n_frames = int(v[0])
+        t_idx = np.arange(self.n_frames)
+        frame_ct = (v[None, :] > t_idx[:, None]).sum(1).astype(np.int32)          # ct_i
+        frame_off = np.concatenate([[0], np.cumsum(frame_ct)[:-1]]).astype(np.int64)
+        self.n_img = int(frame_ct.sum())
+        img_of = np.full((B, T), -1, dtype=np.int32)
+        img_frame = np.empty(self.n_img, dtype=np.int32)
+        img_clip = np.empty(self.n_img, dtype=np.int32)
+        for t in range(self.n_frames):
+            ct = int(frame_ct[t])
+            img_of[:ct, t] = frame_off[t] + np.arange(ct)
+            img_frame[frame_off[t]:frame_off[t] + ct] = t
+            img_clip[frame_off[t]:frame_off[t] + ct] = np.arange(ct)
+        film_row = img_frame * B + img_clip       # row of the (n_frames*B, 2*C*NB) FiLM matrix
+        feat_row = img_clip * T + img_frame       # row of the (B*T, A) attention feature matrix
+        packed = np.concatenate([img_of.reshape(-1), img_frame, film_row, feat_row, frame_ct,
+                                 v.astype(np.int32)]).astype(np.int32)
+        dev = torch.from_numpy(packed)
+        if torch.device(device).type == "cuda":
+            dev = dev.pin_memory().to(device, non_blocking=True)
+        o = 0
+        self.img_of = dev[o:o + B * T]; o += B * T
+        self.img_frame = dev[o:o + self.n_img]; o += self.n_img
+        self.film_row = dev[o:o + self.n_img]; o += self.n_img
+        self.feat_row = dev[o:o + self.n_img]; o += self.n_img
+        self.frame_ct = dev[o:o + self.n_frames]; o += self.n_frames
+        self.v_lens32 = dev[o:o + B]
+        self.frame_ct_host = frame_ct
+
+
+class GradSink(dict):
+    """name -> gradient; calls ``hook(name, tensor)`` the moment a gradient is final so that a data-parallel
+    wrapper can start its all-reduce while the rest of the backward pass is still running (videonavqa_b200.dp)."""
+
+    def __init__(self, hook=None):
+        super().__init__()
+        self._hook = hook
+
+    def __setitem__(self, name, tensor):
+        super().__setitem__(name, tensor)
+        if self._hook is not None:
+            self._hook(name, tensor)
+
+
+class WeightCache:
+    """Kernel-friendly repacks of the PyTorch-layout parameters; derived data, rebuilt when a parameter's
+    version counter or storage changes (load_state_dict, optimizer step, .cuda())."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, key, tensor, build):
+        tag = (tensor.data_ptr(), tensor._version, tuple(tensor.shape))
+        hit = self._c.get(key)
+        if hit is None or hit[0] != tag:
+            hit = (tag, build(tensor))
+            self._c[key] = hit
+        return hit[1]
+
+
+def _choose_splits(n_img, k_total):
+    """split-K factor for the fc_embed_attn GEMM: smallest divisor of 130 that fills the SMs."""
+    n_tiles = (n_img + 207) // 208
+    for s in (1, 2, 5, 10, 13, 26, 65, 130):
+        if (k_total // s) % 32 == 0 and n_tiles * s >= 140:
+            return s
+    return 130
+
+
+# ======================================================================================== trunk forward
+def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save, enc_prefix="film_layer.0.",
+                  film_lin_prefix="film_layer.1."):
+    """conv_init+ReLU+BN, question encoder + FiLM generator, FiLM ResBlocks.  Returns (x_last, ctx)."""
+    dev = v_input.device
+    B, c_in = v_input.shape[0], v_input.shape[1]
+    C = P["conv_init.weight"].shape[0]
+    nb = 0
+    while f"film_pipeline.{nb}.weight" in P:
+        nb += 1
+    n_img = plan.n_img
+    ctx = {"plan": plan, "C": C, "nb": nb, "c_in": c_in}
+
+    # K0: frame-image-major NHWC
+    x0 = ops.frames_to_nhwc(v_input, plan.img_of, n_img)
+
+    # ---- question encoder on a side stream (independent of the video until the first FiLM epilogue)
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        w_ih, w_hh = P[enc_prefix + "weight_ih_l0"], P[enc_prefix + "weight_hh_l0"]
+        gx = ops.embed_gates(q_input, q_lens32, P["embed.weight"], w_ih, P[enc_prefix + "bias_ih_l0"],
+                             P[enc_prefix + "bias_hh_l0"])
+        whh_t = cache.get(enc_prefix + "whh_t", w_hh, lambda w: w.t().contiguous())
+        c0 = film_c.clone() if save else None
+        h_pass, sg, sc, sh = ops.lstm_chain_forward(gx, q_lens32, whh_t, film_h, film_c, plan.n_frames, save=save)
+        H = h_pass.shape[-1]
+        film = ops.linear(h_pass.view(plan.n_frames * B, H), P[film_lin_prefix + "weight"], P[film_lin_prefix + "bias"],
+                          relu=True)
+        for t in (gx, h_pass, film, sg, sc, sh, c0):
+            if t is not None:
+                t.record_stream(main)   # allocated on the side stream, consumed on the main stream
+    film_ready = torch.cuda.Event()
+    film_ready.record(side)
+
+    # ---- conv_init -> ReLU -> BatchNorm (:211)
+    w_init = cache.get("conv_init", P["conv_init.weight"], ops.pack_conv_weight)
+    if training:
+        y0 = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=torch.float32)
+        stat = torch.zeros(2, plan.n_frames, C, device=dev, dtype=torch.float64)
+        ops.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_STATS, out=y0,
+                      bias=P["conv_init.bias"], img_frame=plan.img_frame, stat_sum=stat[0], stat_sq=stat[1])
+        scale, shift, mean, rstd = ops.bn_finalize_train(stat[0], stat[1], plan.frame_ct, plan.n_frames,
+                                                         P["bn_init.weight"], P["bn_init.bias"], bn["running_mean"],
+                                                         bn["running_var"], BN_MOMENTUM, BN_EPS)
+        bn["num_batches_tracked"] += plan.n_frames
+        x = ops.bn_apply(y0, plan.img_frame, scale, shift)
+        ctx.update(y0=y0, mean=mean, rstd=rstd)
+    else:
+        scale, shift = ops.bn_eval_affine(P["bn_init.weight"], P["bn_init.bias"], bn["running_mean"],
+                                          bn["running_var"], BN_EPS)
+        x = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=torch.float32)
+        ops.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_AFFINE, out=x,
+                      bias=P["conv_init.bias"], scale=scale, shift=shift)
+
+    # ---- FiLM ResBlocks (:217-241)
+    xs, ress, zs = [x], [], []
+    for k in range(nb):
+        w1 = cache.get(f"c1x1.{k}", P[f"conv1x1_layers.{k}.weight"], ops.pack_conv_weight)
+        w3 = cache.get(f"c3x3.{k}", P[f"film_pipeline.{k}.weight"], ops.pack_conv_weight)
+        res = torch.empty_like(x)
+        ops.conv_gemm(w1, x, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_BIAS_RELU, out=res,
+                      bias=P[f"conv1x1_layers.{k}.bias"])
+        if k == 0:
+            main.wait_event(film_ready)
+        z = torch.empty_like(x) if save else None
+        out = torch.empty_like(x)
+        ops.conv_gemm(w3, res, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_FILM, out=out,
+                      bias=P[f"film_pipeline.{k}.bias"], film=film, film_row=plan.film_row, film_ld=film.stride(0),
+                      alpha_off=2 * k * C, res=res, z_out=z)
+        x = out
+        if save:
+            xs.append(x); ress.append(res); zs.append(z)
+    if nb == 0:
+        main.wait_event(film_ready)
+    if save:
+        ctx.update(x0=x0, xs=xs, ress=ress, zs=zs, film=film, h_pass=h_pass, gx=gx, sg=sg, sc=sc, sh=sh, c0=c0,
+                   enc_prefix=enc_prefix, film_lin_prefix=film_lin_prefix)
+    return x, ctx
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
+# ======================================================================================== trunk backward
+def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads):
+    """Backward of trunk_forward given d(loss)/d(x_last); fills `grads` (name -> tensor)."""
+    plan, C, nb, c_in = ctx["plan"], ctx["C"], ctx["nb"], ctx["c_in"]
+    n_img, B = plan.n_img, plan.B
+    dev = dx_last.device
+    film = ctx["film"]
+    dfilm = torch.zeros_like(film)
+    dout = dx_last
+    for k in reversed(range(nb)):
+        res, z, x_in = ctx["ress"][k], ctx["zs"][k], ctx["xs"][k]
+        db3 = torch.zeros(C, device=dev, dtype=torch.float32)
+        dz = ops.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3)
+        grads[f"film_pipeline.{k}.bias"] = db3
+        dw3 = torch.zeros_like(P[f"film_pipeline.{k}.weight"])
+        ops.conv_wgrad(dz, res, dw3, n_img=n_img, cout=C, cin=C, taps=9)
+        grads[f"film_pipeline.{k}.weight"] = dw3
+        w3t = cache.get(f"c3x3t.{k}", P[f"film_pipeline.{k}.weight"], lambda w: ops.pack_conv_weight(w, True))
+        db1 = torch.zeros(C, device=dev, dtype=torch.float32)
+        dpre = torch.empty_like(res)
+        ops.conv_gemm(w3t, dz, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_DGRAD_RES, out=dpre, add=dout, res=res,
+                      dbias=db1)
+        del dz
+        grads[f"conv1x1_layers.{k}.bias"] = db1
+        dw1 = torch.zeros_like(P[f"conv1x1_layers.{k}.weight"])
+        ops.conv_wgrad(dpre, x_in, dw1, n_img=n_img, cout=C, cin=C, taps=1)
+        grads[f"conv1x1_layers.{k}.weight"] = dw1
+        w1t = cache.get(f"c1x1t.{k}", P[f"conv1x1_layers.{k}.weight"], lambda w: ops.pack_conv_weight(w, True))
+        dx = torch.empty_like(res)
+        ops.conv_gemm(w1t, dpre, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_PLAIN, out=dx)
+        del dpre
+        dout = dx
+    # ---- BatchNorm + ReLU + conv_init
+    db0 = torch.zeros(C, device=dev, dtype=torch.float32)
+    dgamma = torch.zeros(C, device=dev, dtype=torch.float32)
+    dbeta = torch.zeros(C, device=dev, dtype=torch.float32)
+    dy0 = ops.bn_backward(dout, ctx["y0"], plan.img_frame, plan.frame_ct, plan.n_frames, ctx["mean"], ctx["rstd"],
+                          P["bn_init.weight"], db0, dgamma, dbeta)
+    grads["conv_init.bias"] = db0
+    grads["bn_init.weight"] = dgamma
+    grads["bn_init.bias"] = dbeta
+    dw0 = torch.zeros_like(P["conv_init.weight"])
+    ops.conv_wgrad(dy0, ctx["x0"], dw0, n_img=n_img, cout=C, cin=c_in, taps=9)
+    grads["conv_init.weight"] = dw0
+    # ---- FiLM generator: Linear+ReLU (mask already applied by film_backward) and the chained LSTM
+    enc, lin = ctx["enc_prefix"], ctx["film_lin_prefix"]
+    h_pass = ctx["h_pass"]
+    H = h_pass.shape[-1]
+    hp2 = h_pass.view(plan.n_frames * B, H)
+    grads[lin + "weight"] = ops.linear_wgrad(dfilm, hp2)
+    grads[lin + "bias"] = ops.colsum(dfilm)
+    dh_pass = ops.linear_dgrad(dfilm, P[lin + "weight"])
+    question_backward(P, ctx, dh_pass, q_input, q_lens32, grads, enc)
+
+
+def question_backward(P, ctx, dh_pass, q_input, q_lens32, grads, enc):
+    """BPTT through the chained question LSTM + embedding (autograd of compute_film_values, :144-171)."""
+    sg, sc, sh = ctx["sg"], ctx["sc"], ctx["sh"]
+    n_pass, B, L, H4 = sg.shape
+    H = H4 // 4
+    dgates, dgx = ops.lstm_chain_backward(dh_pass, q_lens32, P[enc + "weight_hh_l0"], sg, sc, ctx["c0"])
+    steps = n_pass * B * L
+    grads[enc + "weight_hh_l0"] = ops.linear_wgrad(dgates.view(steps, H4), sh.view(steps, H), ksplit=64)
+    dgx2 = dgx.view(B * L, H4)
+    xemb = ops.embed_gather(q_input, q_lens32, P["embed.weight"])
+    E = xemb.shape[-1]
+    grads[enc + "weight_ih_l0"] = ops.linear_wgrad(dgx2, xemb.view(B * L, E), ksplit=8)
+    bsum = ops.colsum(dgx2)
+    grads[enc + "bias_ih_l0"] = bsum
+    grads[enc + "bias_hh_l0"] = bsum.clone()
+    dxemb = ops.linear_dgrad(dgx2, P[enc + "weight_ih_l0"])
+    dembed = torch.zeros_like(P["embed.weight"])
+    ops.embed_backward(q_input, q_lens32, dxemb, dembed)
+    grads["embed.weight"] = dembed
+
+
+# ======================================================================================== attention model
+def attn_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, T, training, save):
+    """FiLMAttnPretrainedStem.forward (models/film_attn_pt_stem.py:188-301)."""
+    dev = v_input.device
+    B = v_input.shape[0]
+    plan = Plan(v_lens_host, B, T, dev)
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
+    C, n_img = ctx["C"], plan.n_img
+    A = P["fc_attn_1.weight"].shape[1]
+    # fc_embed_attn over the NHWC-flattened map (:244): split-K tensor-core GEMM + reduction that scatters each
+    # frame image to its (clip, frame) row of the zero-padded feature matrix (:245-256)
+    wfc = cache.get("fc_embed", P["fc_embed_attn.weight"], lambda w: ops.permute_fc_weight(w, C))
+    K = IMG_PIX * C
+    splits = _choose_splits(n_img, K)
+    partial = torch.empty(splits, n_img, A, device=dev, dtype=torch.float32)
+    ops.conv_gemm(wfc, x, taps=1, cin=K // splits, cout=A, n_img=n_img, epi=EPI_PARTIAL, out=partial, flat=True,
+                  x_ld=K, splits=splits)
+    feats = torch.zeros(B, T, A, device=dev, dtype=torch.float32)
+    ops.splitk_reduce(partial, splits, n_img, A, P["fc_embed_attn.bias"], plan.feat_row, feats)
+    wih_t = cache.get("tail_wih_t", P["lstm_attn.weight_ih"], lambda w: w.t().contiguous())
+    whh_t = cache.get("tail_whh_t", P["lstm_attn.weight_hh"], lambda w: w.t().contiguous())
+    hs, coefs, cx, gates, cs = ops.attn_tail_forward(
+        feats, plan.v_lens32, plan.n_frames, P["fc_attn_1.weight"], P["fc_attn_1.bias"], P["fc_hidden_attn.weight"],
+        P["fc_hidden_attn.bias"], wih_t, whh_t, P["lstm_attn.bias_ih"], P["lstm_attn.bias_hh"], save=save)
+    logits = ops.linear(hs.view(B, T * A), P["out_linear.weight"], P["out_linear.bias"])
+    if save:
+        ctx.update(feats=feats, hs=hs, coefs=coefs, cx=cx, gates=gates, cs=cs, A=A, T=T, x_last=x)
+    return logits, ctx
+
+
+def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+    plan, C, A, T = ctx["plan"], ctx["C"], ctx["A"], ctx["T"]
+    B, n_img = plan.B, plan.n_img
+    dev = dlogits.device
+    grads = GradSink(grad_hook)
+    hs = ctx["hs"]
+    hs2 = hs.view(B, T * A)
+    dlogits = dlogits.contiguous()
+    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, hs2)
+    grads["out_linear.bias"] = ops.colsum(dlogits)
+    dhs = ops.linear_dgrad(dlogits, P["out_linear.weight"]).view(B, T, A)
+    dw1 = torch.zeros_like(P["fc_attn_1.weight"]); db1 = torch.zeros_like(P["fc_attn_1.bias"])
+    dwh = torch.zeros_like(P["fc_hidden_attn.weight"]); dbh = torch.zeros_like(P["fc_hidden_attn.bias"])
+    dfeats, dgates = ops.attn_tail_backward(ctx["feats"], plan.v_lens32, plan.n_frames, P["fc_attn_1.weight"],
+                                            P["fc_hidden_attn.weight"], P["lstm_attn.weight_ih"],
+                                            P["lstm_attn.weight_hh"], hs, ctx["coefs"], ctx["gates"], ctx["cs"], dhs,
+                                            dw1, db1, dwh, dbh)
+    for n_, t_ in (("fc_attn_1.weight", dw1), ("fc_attn_1.bias", db1), ("fc_hidden_attn.weight", dwh),
+                   ("fc_hidden_attn.bias", dbh)):
+        grads[n_] = t_
+    dg2 = dgates.view(B * T, 4 * A)
+    grads["lstm_attn.weight_ih"] = ops.linear_wgrad(dg2, ctx["cx"].view(B * T, A))
+    hprev = torch.zeros_like(hs)
+    hprev[:, 1:].copy_(hs[:, :-1])               # data movement only: h_{i-1} with h_{-1} = 0
+    grads["lstm_attn.weight_hh"] = ops.linear_wgrad(dg2, hprev.view(B * T, A))
+    bsum = ops.colsum(dg2)
+    grads["lstm_attn.bias_ih"] = bsum
+    grads["lstm_attn.bias_hh"] = bsum.clone()
+    # fc_embed_attn backward on the valid (clip, frame) rows
+    df_rows = ops.gather_rows(dfeats.view(B * T, A), plan.feat_row, n_img, A, round_tf32=True)
+    grads["fc_embed_attn.bias"] = ops.colsum(df_rows)
+    K = IMG_PIX * C
+    x_last = ctx["x_last"].view(n_img, K)
+    dwp = torch.zeros(A, K, device=dev, dtype=torch.float32)
+    ops.conv_wgrad(df_rows, x_last, dwp, n_img=n_img, cout=A, cin=K, taps=1, flat=True)
+    grads["fc_embed_attn.weight"] = ops.permute_fc_weight(dwp, C, inverse=True)
+    wfc = cache.get("fc_embed", P["fc_embed_attn.weight"], lambda w: ops.permute_fc_weight(w, C))
+    wfc_t = cache.get("fc_embed_t", P["fc_embed_attn.weight"],
+                      lambda w: ops.pack_matrix(ops.permute_fc_weight(w, C, n_pad=w.shape[0]), transpose=True))
+    del wfc
+    dx_last = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=torch.float32)
+    ops.conv_gemm(wfc_t, df_rows, taps=1, cin=A, cout=K, n_img=n_img, epi=EPI_PLAIN, out=dx_last, flat=True, x_ld=A)
+    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
+    return grads
+
+
+# ======================================================================================== global-pooling model
+def gp_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, training, save):
+    """FiLMGlobalPoolingPretrainedStem.forward (models/film_global_pooling_pt_stem.py:180-238)."""
+    dev = v_input.device
+    B, T = v_input.shape[0], v_input.shape[-1]
+    plan = Plan(v_lens_host, B, T, dev)
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
+    C, n_img = ctx["C"], plan.n_img
+    tail = P["c1x1_tail.weight"].shape[0]
+    wt = cache.get("c1x1_tail", P["c1x1_tail.weight"], ops.pack_conv_weight)
+    y = torch.empty(n_img, IMG_PIX, tail, device=dev, dtype=torch.float32)
+    ops.conv_gemm(wt, x, taps=1, cin=C, cout=tail, n_img=n_img, epi=EPI_BIAS_RELU, out=y, bias=P["c1x1_tail.bias"],
+                  no_round=True)
+    pooled, arg = ops.gp_maxpool(y, plan.img_of, B, T, tail)
+    logits = ops.linear(pooled, P["out_linear.weight"], P["out_linear.bias"])
+    if save:
+        ctx.update(pooled=pooled, arg=arg, tail=tail, x_last=x)
+    return logits, ctx
+
+
+def gp_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+    plan, C, tail = ctx["plan"], ctx["C"], ctx["tail"]
+    B, n_img = plan.B, plan.n_img
+    dev = dlogits.device
+    grads = GradSink(grad_hook)
+    dlogits = dlogits.contiguous()
+    pooled = ctx["pooled"]
+    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, pooled)
+    grads["out_linear.bias"] = ops.colsum(dlogits)
+    dpooled = ops.linear_dgrad(dlogits, P["out_linear.weight"])
+    dy = ops.gp_maxpool_backward(dpooled, pooled, ctx["arg"], B, tail, n_img)     # through max + ReLU
+    dy2 = dy.view(n_img * IMG_PIX, tail)
+    grads["c1x1_tail.bias"] = ops.colsum(dy2)
+    x_last = ctx["x_last"]
+    # tail conv gradients: tail is tiny (<= 64 channels) -> fp32 SGEMMs
+    grads["c1x1_tail.weight"] = ops.linear_wgrad(dy2, x_last.view(n_img * IMG_PIX, C), ksplit=32).view(tail, C, 1, 1)
+    dx_last = ops.linear_dgrad(dy2, P["c1x1_tail.weight"].view(tail, C)).view(n_img, IMG_PIX, C)
+    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
+    return grads

@@ -1,0 +1,5 @@
+"""Drop-in replacements for the reference's ``models`` package (hot-path classes only)."""
+from .film_attn_pt_stem import FiLMAttnPretrainedStem
+from .film_global_pooling_pt_stem import FiLMGlobalPoolingPretrainedStem
+
+__all__ = ["FiLMAttnPretrainedStem", "FiLMGlobalPoolingPretrainedStem"]

@@ -1,0 +1,134 @@
+"""Shared machinery of the drop-in modules: parameter containers with the reference's registration order and
+initialisation, the autograd bridge into videonavqa_b200.engine, and the carried question-LSTM state."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import engine, ops
+
+
+def reference_init(module):
+    """The reference's weights_init (models/film_attn_pt_stem.py:111-127): Xavier-uniform weight + zero bias
+    for every Linear / Conv2d; LSTM: Xavier W_ih, orthogonal W_hh, zero b_ih, forget-gate slice of the biases = 1."""
+    if isinstance(module, (nn.Linear, nn.Conv2d)):
+        nn.init.xavier_uniform_(module.weight.data)
+        module.bias.data.zero_()
+    if isinstance(module, nn.LSTM):
+        nn.init.xavier_uniform_(module.weight_ih_l0)
+        nn.init.orthogonal_(module.weight_hh_l0)
+        hidden = module.hidden_size
+        with torch.no_grad():
+            module.bias_hh_l0[hidden:2 * hidden] = 1.0
+            module.bias_ih_l0.zero_()
+
+
+class _FilmFunction(torch.autograd.Function):
+    """One autograd node for the whole hot path: forward and backward are hand-written CUDA pipelines."""
+
+    @staticmethod
+    def forward(ctx, mod, need_grad, v_input, q_input, v_lens, q_lens, *params):
+        ctx.set_materialize_grads(False)
+        P = dict(zip(mod._param_names, params))
+        logits, saved = mod._forward_impl(P, v_input, q_input, v_lens, q_lens, save=need_grad)
+        ctx.mod, ctx.saved, ctx.P = mod, saved, P
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        mod = ctx.mod
+        if dlogits is None:
+            return (None,) * (6 + len(mod._param_names))
+        grads = mod._backward_impl(ctx.P, ctx.saved, dlogits)
+        hook = getattr(mod, "_grad_hook", None)
+        if hook is not None and hasattr(hook, "wait"):
+            hook.wait()     # in-flight gradient all-reduces (videonavqa_b200.dp) must land before autograd reads them
+        ctx.saved = None
+        return (None,) * 6 + tuple(grads.get(n) for n in mod._param_names)
+
+
+class FilmModuleBase(nn.Module):
+    """Behaviour common to FiLMAttnPretrainedStem / FiLMGlobalPoolingPretrainedStem (and the multi-hop variant)."""
+
+    kind = "?"
+
+    # ---- parameter plumbing -------------------------------------------------------------------------------
+    def _collect_params(self):
+        """(names, tensors): registered parameters in registration order, then the unregistered conv1x1_layers
+        (quirk Q1: they are not in state_dict()/parameters() but take part in forward and receive .grad)."""
+        names, tensors = [], []
+        for n, p in self.named_parameters():
+            names.append(n)
+            tensors.append(p)
+        for k, conv in enumerate(self.conv1x1_layers):
+            names += [f"conv1x1_layers.{k}.weight", f"conv1x1_layers.{k}.bias"]
+            tensors += [conv.weight, conv.bias]
+        return names, tensors
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        # The reference moves conv1x1_layers / film_hidden to the GPU by hand at construction
+        # (film_attn_pt_stem.py:102-103,137-138); follow the module so that .cuda() after construction also works.
+        for conv in getattr(self, "conv1x1_layers", []):
+            conv._apply(fn)
+        fh = getattr(self, "film_hidden", None)
+        if fh is not None:
+            self.film_hidden = (fn(fh[0]), fn(fh[1]))
+        return out
+
+    def init_hidden(self):
+        """Reset the carried question-LSTM state (models/film_attn_pt_stem.py:133-138)."""
+        dev = self.embed.weight.device
+        self.film_hidden = (torch.zeros(1, self.batch_size, self.hidden_size, device=dev),
+                            torch.zeros(1, self.batch_size, self.hidden_size, device=dev))
+
+    # ---- forward --------------------------------------------------------------------------------------------
+    def _check_inputs(self, v_input, q_input, v_lens, q_lens):
+        if not v_input.is_cuda:
+            raise RuntimeError("videonavqa_b200 modules run on a CUDA sm_100 device only (no CPU fallback); "
+                               "move the module and its inputs to the GPU")
+        if v_input.shape[0] != self.batch_size:
+            raise RuntimeError(f"batch size {v_input.shape[0]} != constructor batch_size {self.batch_size} "
+                               "(the module is batch-size-locked like the reference, SURVEY Q7)")
+        if tuple(v_input.shape[2:4]) != (10, 13):
+            raise RuntimeError("stem feature maps must be 10 x 13 (hard-coded 130 in the reference)")
+
+    def forward(self, v_input, q_input, v_lens, q_lens):
+        self._check_inputs(v_input, q_input, v_lens, q_lens)
+        ops.device_check()
+        names, tensors = self._collect_params()
+        self._param_names = names
+        need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        return _FilmFunction.apply(self, need_grad, v_input.float().contiguous(), q_input, v_lens, q_lens, *tensors)
+
+    def _prepare(self, v_input, q_input, v_lens, q_lens):
+        dev = v_input.device
+        lens = torch.stack([v_lens.to(dev).long(), q_lens.to(dev).long()]).cpu()     # the one host sync
+        v_host, q_host = lens[0].tolist(), lens[1].tolist()
+        L = q_input.shape[1]
+        if min(q_host) < 1 or max(q_host) > L:
+            raise ValueError(f"q_lens must lie in [1, {L}]")
+        q_lens_dev = q_lens.to(dev).long()
+        q_lens32 = q_lens_dev.to(torch.int32)
+        # film_hidden is kept in q_len-sorted order like the reference (film_attn_pt_stem.py:153-160)
+        perm = q_lens_dev.sort(0, descending=True)[1]
+        h = torch.empty(self.batch_size, self.hidden_size, device=dev)
+        c = torch.empty_like(h)
+        h[perm] = self.film_hidden[0][0].to(dev).detach()
+        c[perm] = self.film_hidden[1][0].to(dev).detach()
+        return v_host, q_lens32, perm, h, c, q_input.to(dev).long().contiguous()
+
+    def _bn_state(self):
+        return {"running_mean": self.bn_init.running_mean, "running_var": self.bn_init.running_var,
+                "num_batches_tracked": self.bn_init.num_batches_tracked}
+
+    def _finish(self, perm, h, c):
+        self.film_hidden = (h[perm].unsqueeze(0), c[perm].unsqueeze(0))
+
+    @property
+    def _cache(self):
+        c = self.__dict__.get("_weight_cache")
+        if c is None:
+            c = engine.WeightCache()
+            self.__dict__["_weight_cache"] = c
+        return c

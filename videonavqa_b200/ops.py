@@ -1,0 +1,326 @@
+"""Torch-tensor wrappers over the C ABI (include/vnqa_b200.h).  PyTorch is used for device memory and the
+current stream only; all arithmetic happens in libvnqa_b200.so."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs
+from ._lib import check as _check
+
+IMG_PIX = 130
+_KERNELS_PER_CALL = {"bn_backward": 3, "vnqa_device_check": 0}   # entry points that launch != 1 kernel
+
+
+def check(rc, what):
+    _check(rc, what)
+    _count(_KERNELS_PER_CALL.get(what, 1))
+
+# ---- measurement hooks (bench.py): kernel-launch counter and optional per-launch CUDA-event timing of the
+# tensor-core kernels on the stream they are launched on.  Off by default; they never change what is computed.
+LAUNCHES = 0
+PROFILE = None      # list of (tag, flops, start_event, end_event) when enabled
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _timed:
+    def __init__(self, tag, flops):
+        self.tag, self.flops = tag, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.tag, self.flops, self.e0, self.e1))
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "videonavqa_b200 ops need CUDA tensors (no CPU fallback)"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    assert t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    return t
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def device_check():
+    check(_lib.lib().vnqa_device_check(), "vnqa_device_check")
+
+
+# ------------------------------------------------------------------------------------------ layout / packing
+def frames_to_nhwc(v_input, img_of, n_img):
+    B, C, H, W, T = v_input.shape
+    assert (H, W) == (10, 13)
+    x = torch.empty(n_img, IMG_PIX, C, device=v_input.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_frames_to_nhwc(_p(_f32c(v_input)), _p(x), _p(img_of), B, C, T, _stream()), "frames_to_nhwc")
+    return x
+
+
+def pack_conv_weight(w, transpose_flip=False):
+    """(Cout, Cin, kh, kw) -> [taps][rows_pad][K] tf32-rounded; transpose_flip builds the dgrad operand."""
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3]
+    rows = cin if transpose_flip else cout
+    K = cout if transpose_flip else cin
+    rows_pad = round_up(rows, 128)
+    out = torch.empty(taps, rows_pad, K, device=w.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_pack_conv_weight(_p(_f32c(w)), _p(out), cout, cin, taps, rows_pad, int(transpose_flip),
+                                           _stream()), "pack_conv_weight")
+    return out
+
+
+def pack_matrix(w, transpose=False):
+    """Linear weight (N, K) as a 1-tap 'convolution' operand: [rows_pad][K] (or its transpose [K_pad][N])."""
+    n, k = w.shape
+    return pack_conv_weight(w.view(n, k, 1, 1), transpose_flip=transpose)[0]
+
+
+def permute_fc_weight(w, C, inverse=False, n_pad=None):
+    n = w.shape[0]
+    n_pad = n if inverse else (n_pad or round_up(n, 128))
+    out = torch.empty(n if inverse else n_pad, C * IMG_PIX, device=w.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_permute_fc_weight(_p(_f32c(w)), _p(out), n, n_pad, C, int(inverse), _stream()),
+          "permute_fc_weight")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ tensor-core GEMMs
+def conv_gemm(w_packed, x, *, taps, cin, cout, n_img, epi, out, flat=False, x_ld=0, splits=1, no_round=False,
+              bias=None, scale=None, shift=None, img_frame=None, stat_sum=None, stat_sq=None, film=None,
+              film_row=None, film_ld=0, alpha_off=0, res=None, z_out=None, add=None, dbias=None):
+    a = ConvArgs()
+    a.w_packed = w_packed.data_ptr()
+    a.x = x.data_ptr()
+    a.taps, a.cin, a.cout, a.rows_pad, a.n_img = taps, cin, cout, round_up(cout, 128), n_img
+    a.flat, a.x_ld, a.splits, a.epi, a.no_round = int(flat), x_ld, splits, epi, int(no_round)
+    a.out = out.data_ptr()
+    for name, t in (("bias", bias), ("scale", scale), ("shift", shift), ("img_frame", img_frame),
+                    ("stat_sum", stat_sum), ("stat_sq", stat_sq), ("film", film), ("film_row", film_row),
+                    ("res", res), ("z_out", z_out), ("add", add), ("dbias", dbias)):
+        setattr(a, name, t.data_ptr() if t is not None else None)
+    a.film_ld, a.alpha_off = film_ld, alpha_off
+    rows = n_img if flat else n_img * IMG_PIX
+    tag = f"conv_gemm.{'flat' if flat else str(taps) + 'tap'}.epi{epi}.k{cin * splits}.n{cout}"
+    with _timed(tag, 2.0 * rows * cout * cin * splits * taps):
+        check(_lib.lib().vnqa_conv_gemm(ctypes.byref(a), _stream()), "conv_gemm")
+    return out
+
+
+def conv_wgrad(dy, x, dw, *, n_img, cout, cin, taps, flat=False):
+    rows = n_img if flat else n_img * IMG_PIX
+    tag = f"conv_wgrad.{'flat' if flat else str(taps) + 'tap'}.k{cin}.n{cout}"
+    with _timed(tag, 2.0 * rows * cout * cin * taps):
+        check(_lib.lib().vnqa_conv_wgrad(_p(dy), _p(x), _p(dw), n_img, cout, cin, taps, int(flat), _stream()),
+              "conv_wgrad")
+    return dw
+
+
+# ------------------------------------------------------------------------------------------ small fp32 ops
+def sgemm(a, b, *, M, N, K, a_strides, b_strides, out=None, bias=None, relu=False, accumulate=False, ksplit=1):
+    """out[M][N] = A B^T (+bias, relu); A(m,k) = a[m*rs + k*cs], B(n,k) likewise."""
+    if out is None:
+        out = (torch.zeros if ksplit > 1 else torch.empty)(M, N, device=a.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_sgemm(_p(a), _p(b), _p(out), _p(bias), M, N, K, a_strides[0], a_strides[1], b_strides[0],
+                                b_strides[1], out.stride(0), int(relu), int(accumulate), ksplit, _stream()), "sgemm")
+    return out
+
+
+def linear(x, w, bias=None, relu=False):
+    """x (M,K) @ w (N,K)^T + bias."""
+    M, K = x.shape
+    N = w.shape[0]
+    return sgemm(x, w, M=M, N=N, K=K, a_strides=(x.stride(0), x.stride(1)), b_strides=(w.stride(0), w.stride(1)),
+                 bias=bias, relu=relu)
+
+
+def linear_dgrad(dy, w):
+    """dy (M,N) @ w (N,K) -> (M,K)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    return sgemm(dy, w, M=M, N=K, K=N, a_strides=(dy.stride(0), dy.stride(1)), b_strides=(w.stride(1), w.stride(0)))
+
+
+def linear_wgrad(dy, x, ksplit=1):
+    """dy (M,N)^T @ x (M,K) -> (N,K)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    return sgemm(dy, x, M=N, N=K, K=M, a_strides=(dy.stride(1), dy.stride(0)), b_strides=(x.stride(1), x.stride(0)),
+                 ksplit=ksplit)
+
+
+def colsum(x):
+    rows, n = x.shape
+    out = torch.empty(n, device=x.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_colsum(_p(x), rows, n, x.stride(0), _p(out), 0, _stream()), "colsum")
+    return out
+
+
+def bn_finalize_train(stat_sum, stat_sq, frame_ct, n_frames, gamma, beta, running_mean, running_var, momentum, eps):
+    C = gamma.numel()
+    dev = gamma.device
+    scale, shift, mean, rstd = (torch.empty(n_frames, C, device=dev, dtype=torch.float32) for _ in range(4))
+    check(_lib.lib().vnqa_bn_finalize_train(_p(stat_sum), _p(stat_sq), _p(frame_ct), n_frames, C, _p(gamma), _p(beta),
+                                            _p(running_mean), _p(running_var), momentum, eps, _p(scale), _p(shift),
+                                            _p(mean), _p(rstd), _stream()), "bn_finalize_train")
+    return scale, shift, mean, rstd
+
+
+def bn_eval_affine(gamma, beta, running_mean, running_var, eps):
+    C = gamma.numel()
+    scale = torch.empty(C, device=gamma.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    check(_lib.lib().vnqa_bn_eval_affine(_p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, C, _p(scale),
+                                         _p(shift), _stream()), "bn_eval_affine")
+    return scale, shift
+
+
+def bn_apply(y, img_frame, scale, shift):
+    n_img, _, C = y.shape
+    x = torch.empty_like(y)
+    check(_lib.lib().vnqa_bn_apply(_p(y), _p(x), _p(img_frame), _p(scale), _p(shift), n_img, C, _stream()), "bn_apply")
+    return x
+
+
+def bn_backward(dx, y, img_frame, frame_ct, n_frames, mean, rstd, gamma, dbias, dgamma, dbeta):
+    n_img, _, C = y.shape
+    s1 = torch.empty(n_frames, C, device=y.device, dtype=torch.float32)
+    s2 = torch.empty_like(s1)
+    dy = torch.empty_like(y)
+    check(_lib.lib().vnqa_bn_backward(_p(dx), _p(y), _p(img_frame), _p(frame_ct), n_frames, _p(mean), _p(rstd),
+                                      _p(gamma), n_img, C, _p(s1), _p(s2), _p(dy), _p(dbias), _p(dgamma), _p(dbeta),
+                                      _stream()), "bn_backward")
+    return dy
+
+
+def film_backward(dout, z, film, film_row, alpha_off, dfilm, dbias):
+    n_img, _, C = z.shape
+    dz = torch.empty_like(z)
+    check(_lib.lib().vnqa_film_backward(_p(dout), _p(z), _p(film), _p(film_row), film.stride(0), alpha_off, n_img, C,
+                                        _p(dz), _p(dfilm), _p(dbias), _stream()), "film_backward")
+    return dz
+
+
+def splitk_reduce(partial, splits, rows, N, bias, dst_row, out):
+    check(_lib.lib().vnqa_splitk_reduce(_p(partial), splits, rows, N, _p(bias), _p(dst_row), _p(out), _stream()),
+          "splitk_reduce")
+    return out
+
+
+def gather_rows(src, src_row, rows, N, round_tf32=False):
+    out = torch.empty(rows, N, device=src.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_gather_rows(_p(src), _p(src_row), rows, N, _p(out), int(round_tf32), _stream()), "gather_rows")
+    return out
+
+
+def gp_maxpool(y, img_of, B, T, tail):
+    pooled = torch.empty(B, tail * IMG_PIX, device=y.device, dtype=torch.float32)
+    arg = torch.empty(B, tail * IMG_PIX, device=y.device, dtype=torch.int32)
+    check(_lib.lib().vnqa_gp_maxpool(_p(y), _p(img_of), B, T, tail, _p(pooled), _p(arg), _stream()), "gp_maxpool")
+    return pooled, arg
+
+
+def gp_maxpool_backward(dpooled, pooled, arg, B, tail, n_img):
+    dy = torch.zeros(n_img, IMG_PIX, tail, device=pooled.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_gp_maxpool_backward(_p(dpooled), _p(pooled), _p(arg), B, tail, _p(dy), _stream()),
+          "gp_maxpool_backward")
+    return dy
+
+
+# ------------------------------------------------------------------------------------------ question encoder
+def embed_gates(q_input, q_lens32, embed, w_ih, b_ih, b_hh):
+    B, L = q_input.shape
+    E = embed.shape[1]
+    H = w_ih.shape[0] // 4
+    gx = torch.zeros(B, L, 4 * H, device=embed.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_embed_gates(_p(q_input), _p(q_lens32), _p(embed), _p(w_ih), _p(b_ih), _p(b_hh), B, L, E, H,
+                                      _p(gx), _stream()), "embed_gates")
+    return gx
+
+
+def lstm_chain_forward(gx, q_lens32, whh_t, h_state, c_state, n_pass, save=False):
+    B, L, H4 = gx.shape
+    H = H4 // 4
+    dev = gx.device
+    h_pass = torch.empty(n_pass, B, H, device=dev, dtype=torch.float32)
+    sg = sc = sh = None
+    if save:
+        sg = torch.zeros(n_pass, B, L, H4, device=dev, dtype=torch.float32)
+        sc = torch.zeros(n_pass, B, L, H, device=dev, dtype=torch.float32)
+        sh = torch.zeros(n_pass, B, L, H, device=dev, dtype=torch.float32)
+    check(_lib.lib().vnqa_lstm_chain_forward(_p(gx), _p(q_lens32), _p(whh_t), _p(h_state), _p(c_state), n_pass, B, L, H,
+                                             _p(h_pass), _p(sg), _p(sc), _p(sh), _stream()), "lstm_chain_forward")
+    return h_pass, sg, sc, sh
+
+
+def lstm_chain_backward(dh_pass, q_lens32, whh, save_gates, save_c, c0):
+    n_pass, B, L, H4 = save_gates.shape
+    H = H4 // 4
+    dgates = torch.zeros_like(save_gates)
+    dgx = torch.empty(B, L, H4, device=whh.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_lstm_chain_backward(_p(dh_pass), _p(q_lens32), _p(whh), _p(save_gates), _p(save_c), _p(c0),
+                                              n_pass, B, L, H, _p(dgates), _p(dgx), _stream()), "lstm_chain_backward")
+    return dgates, dgx
+
+
+def embed_gather(q_input, q_lens32, embed):
+    B, L = q_input.shape
+    E = embed.shape[1]
+    x = torch.empty(B, L, E, device=embed.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_embed_gather(_p(q_input), _p(q_lens32), _p(embed), B, L, E, _p(x), _stream()), "embed_gather")
+    return x
+
+
+def embed_backward(q_input, q_lens32, dx, dembed):
+    B, L = q_input.shape
+    check(_lib.lib().vnqa_embed_backward(_p(q_input), _p(q_lens32), _p(dx), B, L, dx.shape[-1], _p(dembed), _stream()),
+          "embed_backward")
+    return dembed
+
+
+# ------------------------------------------------------------------------------------------ attention tail
+def attn_tail_forward(feats, v_lens32, n_proc, w1, b1, wh, bh, wih_t, whh_t, b_ih, b_hh, save=False):
+    B, T, A = feats.shape
+    dev = feats.device
+    hs = torch.empty(B, T, A, device=dev, dtype=torch.float32)
+    coefs = ctxt = gates = cs = None
+    if save:
+        coefs = torch.empty(B, T, T, device=dev, dtype=torch.float32)
+        ctxt = torch.empty(B, T, A, device=dev, dtype=torch.float32)
+        gates = torch.empty(B, T, 4 * A, device=dev, dtype=torch.float32)
+        cs = torch.empty(B, T, A, device=dev, dtype=torch.float32)
+    check(_lib.lib().vnqa_attn_tail_forward(_p(feats), _p(v_lens32), n_proc, B, T, A, _p(w1), _p(b1), _p(wh), _p(bh),
+                                            _p(wih_t), _p(whh_t), _p(b_ih), _p(b_hh), _p(hs), _p(coefs), _p(ctxt),
+                                            _p(gates), _p(cs), _stream()), "attn_tail_forward")
+    return hs, coefs, ctxt, gates, cs
+
+
+def attn_tail_backward(feats, v_lens32, n_proc, w1, wh, wih, whh, hs, coefs, gates, cs, dhs, dw1, db1, dwh, dbh):
+    B, T, A = feats.shape
+    dfeats = torch.empty_like(feats)
+    dgates = torch.empty(B, T, 4 * A, device=feats.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_attn_tail_backward(_p(feats), _p(v_lens32), n_proc, B, T, A, _p(w1), _p(wh), _p(wih), _p(whh),
+                                             _p(hs), _p(coefs), _p(gates), _p(cs), _p(dhs), _p(dfeats), _p(dgates),
+                                             _p(dw1), _p(db1), _p(dwh), _p(dbh), _stream()), "attn_tail_backward")
+    return dfeats, dgates
