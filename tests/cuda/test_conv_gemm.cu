@@ -299,7 +299,12 @@ static int run_case(const Case& c) {
 }
 
 int main(int argc, char** argv) {
-  const bool perf = argc > 1 && !strcmp(argv[1], "--perf");
+  bool perf = false;
+  const char* only = nullptr;   // --case <substring>: run only the matching cases (used under ncu)
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "--perf")) perf = true;
+    if (!strcmp(argv[i], "--case") && i + 1 < argc) only = argv[++i];
+  }
   CKV(vnqa_device_check());
   printf("SMs: %d\n", vnqa_sm_count());
   std::vector<Case> cases = {
@@ -323,7 +328,8 @@ int main(int argc, char** argv) {
     cases.push_back({"P fc_embed splitK", 1, 10240, 128, 2240, 1, 13, VNQA_EPI_PARTIAL, 4096, 10});
   }
   int fails = 0;
-  for (const auto& c : cases) fails += run_case(c);
+  for (const auto& c : cases)
+    if (!only || strstr(c.name, only)) fails += run_case(c);
   printf("%s (%d failing cases)\n", fails ? "FAILED" : "ALL OK", fails);
   return fails ? 1 : 0;
 }

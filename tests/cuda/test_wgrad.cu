@@ -121,7 +121,12 @@ static int run_case(const Case& c) {
 }
 
 int main(int argc, char** argv) {
-  const bool perf = argc > 1 && !strcmp(argv[1], "--perf");
+  bool perf = false;
+  const char* only = nullptr;   // --case <substring>: run only the matching cases (used under ncu)
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "--perf")) perf = true;
+    if (!strcmp(argv[i], "--case") && i + 1 < argc) only = argv[++i];
+  }
   CKV(vnqa_device_check());
   std::vector<Case> cases = {
       {"wgrad1x1_small", 1, 128, 128, 8, 0, 0},
@@ -138,7 +143,8 @@ int main(int argc, char** argv) {
     cases.push_back({"P wgrad fc_embed", 1, 133120, 128, 2240, 1, 5});
   }
   int fails = 0;
-  for (const auto& c : cases) fails += run_case(c);
+  for (const auto& c : cases)
+    if (!only || strstr(c.name, only)) fails += run_case(c);
   printf("%s (%d failing cases)\n", fails ? "FAILED" : "ALL OK", fails);
   return fails ? 1 : 0;
 }
