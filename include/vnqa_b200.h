@@ -97,10 +97,12 @@ typedef struct {
 
 int vnqa_conv_gemm(const vnqa_conv_args* args, void* stream);
 
-/* ---- K4: weight gradient dW[co][ci][tap] += sum_rows dY[row][co] * X[row (+) tap][ci] on tcgen05 (MN-major
- * operands, split-K over pixels, fp32 atomic reduction).  dw must be zero-initialised; layout is PyTorch's
- * (Cout, Cin, kh, kw).  flat != 0: plain dY^T X with dy [n_img][cout], x [n_img][cin]. */
-int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32_t n_img, int32_t cout, int32_t cin,
+/* ---- K4: weight gradient dW[co][ci][tap] = sum_rows dY[row][co] * X[row (+) tap][ci] on tcgen05 (MN-major
+ * operands, split-K over pixels, fp32 atomic reduction).  Output layout is PyTorch's (Cout, Cin, kh, kw).
+ * taps == 1: accumulates into dw, which must be zero-initialised (ws may be NULL).
+ * taps == 9: accumulates into the zero-initialised workspace ws [9][cout][cin] and then overwrites dw.
+ * flat != 0: plain dY^T X with dy [n_img][cout], x [n_img][cin]. */
+int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, float* ws, int32_t n_img, int32_t cout, int32_t cin,
                     int32_t taps, int32_t flat, void* stream);
 
 /* ---- small fp32 GEMM (FFMA, exact fp32): C = [C +] A B^T + bias, optional ReLU.  A(m,k) = a[m*a_rs + k*a_cs],

@@ -46,7 +46,7 @@ SIGNATURES = {
     "vnqa_pack_conv_weight": [P, P, I32, I32, I32, I32, I32, P],
     "vnqa_permute_fc_weight": [P, P, I32, I32, I32, I32, P],
     "vnqa_conv_gemm": [POINTER(ConvArgs), P],
-    "vnqa_conv_wgrad": [P, P, P, I32, I32, I32, I32, I32, P],
+    "vnqa_conv_wgrad": [P, P, P, P, I32, I32, I32, I32, I32, P],
     "vnqa_sgemm": [P, P, P, P, I32, I32, I32, I64, I64, I64, I64, I64, I32, I32, I32, P],
     "vnqa_colsum": [P, I32, I32, I64, P, I32, P],
     "vnqa_bn_finalize_train": [P, P, P, I32, I32, P, P, P, P, F32, F32, P, P, P, P, P],

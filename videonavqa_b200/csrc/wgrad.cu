@@ -9,8 +9,10 @@
 // MN-major) over TMA boxes {32 channels x 104 pixel rows}
 // (104 = 4 images x 2 image rows x 13 = 13 MMA K-steps of 8).  Tap shifts and the zero halo are again TMA box
 // coordinates / out-of-bounds fill.  Tile = 128 (co) x 128 (ci) fp32 accumulators in TMEM, 2 smem stages of
-// 104 KB, split-K over pixel chunks to fill 148 SMs; partial tiles are reduced with fp32 red.global.add into the
-// zero-initialised gradient, written directly in PyTorch (Cout, Cin, kh, kw) layout.
+// 104 KB.  Split-K over pixel chunks, SPLIT-MAJOR tile order: the 148 co-resident CTAs always work on the same
+// pixel range (sized to stay L2-resident), so dY / X are read from DRAM about once instead of once per tile wave.
+// Partial tiles are reduced with fp32 red.global.add, transposed through shared memory so that every warp-level
+// reduction hits 128 contiguous bytes of a [tap][Cout][Cin] buffer; a final pass writes PyTorch's (Cout,Cin,kh,kw).
 #include <cstdlib>
 
 #include "common.h"
@@ -25,22 +27,23 @@ constexpr int WG_A_BYTES = (WG_M / 32) * WG_BOX_BYTES;  // 53248
 constexpr int WG_B_BYTES = (WG_N / 32) * WG_BOX_BYTES;  // 53248
 constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES; // 106496
 constexpr int WG_STAGES = 2;
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_SCRATCH = 4 * 32 * 33 * 4;          // per-epilogue-warp 32x33 transpose tile
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_SCRATCH + 1024 + 256;
 constexpr int WG_THREADS = 256;
 constexpr int WG_TMEM_COLS = 256;                // 2 accumulator stages x 128 columns
 
 struct WParams {
   int taps, m_tiles, n_tiles, splits, n_chunks, chunks_per_split, flat, debug;
   int cout, cin;          // real sizes (tiles beyond are skipped on store)
-  long long out_co_stride, out_ci_stride;  // element strides of the output for (co, ci); tap stride is 1
-  float* out;
+  float* out;             // [taps][cout][cin] accumulation buffer (== dw when taps == 1)
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  float* scratch = reinterpret_cast<float*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES + WG_SCRATCH);
   uint64_t* empty_bar = full_bar + WG_STAGES;
   uint64_t* acc_full = empty_bar + WG_STAGES;
   uint64_t* acc_empty = acc_full + 2;
@@ -64,11 +67,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (p.debug == 3 && blockIdx.x == 0 && (threadIdx.x & 31) == 0)
     printf("wgrad dbg: warp %d past setup, tmem_base %u total_tiles %d chunks %d\n", warp, tmem_base, total_tiles, p.n_chunks);
 
-  // tile -> (mt, nt, tap, split); mt fastest so that concurrently running CTAs share the X (B) slab in L2
+  // tile -> (split, tap, nt, mt), split outermost / mt fastest: one wave of CTAs shares one pixel range, CTAs with the
+  // same nt share the X slab, CTAs with the same mt share the dY slab (all through L2)
+  const int base_tiles = p.m_tiles * p.n_tiles * p.taps;
   auto decode = [&](int tile, int& mt, int& nt, int& tap, int& sp) {
+    sp = tile / base_tiles; tile -= sp * base_tiles;
     mt = tile % p.m_tiles; tile /= p.m_tiles;
-    nt = tile % p.n_tiles; tile /= p.n_tiles;
-    tap = tile % p.taps;   sp = tile / p.taps;
+    nt = tile % p.n_tiles;
+    tap = tile / p.n_tiles;
   };
 
   if (warp == 0) {
@@ -145,21 +151,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&acc_full[as], aphase, 4);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * WG_N;
+      float* tile_s = scratch + ew * (32 * 33);
+      const int co0 = mt * WG_M + ew * 32;           // this warp owns output channels co0 .. co0+31
 #pragma unroll 1
       for (int j0 = 0; j0 < WG_N; j0 += 32) {
         uint32_t v[32];
         tmem_ld_x32(t_base + j0, v);
         tmem_ld_wait();
-        if (co < p.cout) {
-          float* orow = p.out + (long long)co * p.out_co_stride + tap;
+        // lane = co holds 32 consecutive ci: transpose through smem so that a warp reduces 32 consecutive ci of ONE co
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int ci = nt * WG_N + j0 + j;
-            if (ci < p.cin) atomicAdd(orow + (long long)ci * p.out_ci_stride, __uint_as_float(v[j]));
-          }
+        for (int j = 0; j < 32; ++j) tile_s[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int ci = nt * WG_N + j0 + lane;
+        if (ci < p.cin) {
+          float* obase = p.out + ((long long)tap * p.cout + co0) * p.cin + ci;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r)
+            if (co0 + r < p.cout) atomicAdd(obase + (long long)r * p.cin, tile_s[r * 33 + lane]);
         }
         __syncwarp();
       }
+      (void)co;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -176,12 +188,25 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 using namespace vnqa;
 
-// dw must be zero-initialised by the caller (partial tiles are accumulated atomically).
-// conv (flat = 0): dy [n_img][130][cout], x [n_img][130][cin], dw (cout, cin, taps) PyTorch layout.
-// flat = 1: dy [n_rows][cout], x [n_rows][cin], dw (cout, cin) row-major.
-extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32_t n_img, int32_t cout, int32_t cin,
-                               int32_t taps, int32_t flat, void* stream) {
+// [tap][co][ci] -> (co, ci, tap)
+__global__ void wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw, int cout, int cin, int taps) {
+  const long long total = (long long)cout * cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const long long r = i / taps;   // co * cin + ci
+    dw[i] = __ldg(ws + (long long)tap * cout * cin + r);
+  }
+}
+
+// taps == 1: partial tiles are accumulated atomically into dw, which must be zero-initialised by the caller.
+// taps == 9: accumulation happens in ws ([9][cout][cin], zero-initialised by the caller); dw is then overwritten
+//            in PyTorch (cout, cin, 3, 3) layout.
+// conv (flat = 0): dy [n_img][130][cout], x [n_img][130][cin].   flat = 1: dy [n_rows][cout], x [n_rows][cin].
+extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, float* ws, int32_t n_img, int32_t cout,
+                               int32_t cin, int32_t taps, int32_t flat, void* stream) {
   VNQA_REQUIRE(dy && x && dw, "vnqa_conv_wgrad: null pointer");
+  VNQA_REQUIRE(taps == 1 || ws != nullptr, "vnqa_conv_wgrad: 3x3 gradients need the [9][cout][cin] workspace");
   VNQA_REQUIRE(taps == 1 || taps == 9, "vnqa_conv_wgrad: taps must be 1 or 9");
   VNQA_REQUIRE(cout % 32 == 0 && cin % 32 == 0, "vnqa_conv_wgrad: channels must be multiples of 32 (%d, %d)", cout, cin);
   VNQA_REQUIRE(!(flat && taps != 1), "vnqa_conv_wgrad: flat GEMM has one tap");
@@ -194,27 +219,20 @@ extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32
   wp.cout = cout;
   wp.cin = cin;
   wp.n_chunks = flat ? (n_img + WG_KP - 1) / WG_KP : ((n_img + 3) / 4) * 5;
-  wp.out = dw;
-  wp.out_co_stride = (long long)cin * taps;
-  wp.out_ci_stride = taps;
+  wp.out = taps == 1 ? dw : ws;
   const int sms = vnqa_sm_count();
   if (sms <= 0) return -2;
-  // split-K: fill the machine with whole waves
+  // split-K: (a) one split's slice of dY and X (chunks * 104 rows * (cout+cin) * 4 B) should stay L2-resident while
+  // the waves of that split run, (b) there must be enough tiles to fill the SMs, (c) every split owns >= 1 chunk.
   const int base_tiles = wp.m_tiles * wp.n_tiles * taps;
-  int best = 1;
-  double best_eff = -1.0;
-  for (int s = 1; s <= 32 && s <= wp.n_chunks; ++s) {
-    const int cps = (wp.n_chunks + s - 1) / s;
-    const int real = (wp.n_chunks + cps - 1) / cps;   // splits that actually own chunks
-    if (real != s) continue;
-    const int tiles = base_tiles * s;
-    const int waves = (tiles + sms - 1) / sms;
-    double eff = (double)tiles / ((double)waves * sms);
-    if (cps < 8 && s > 1) eff *= 0.5;  // too little work per tile to amortise prologue/epilogue
-    if (eff > best_eff * 1.03) { best_eff = eff; best = s; }
-  }
-  wp.splits = best;
-  wp.chunks_per_split = (wp.n_chunks + best - 1) / best;
+  const double chunk_bytes = (double)WG_KP * 4.0 * ((double)(cout < 1024 ? cout : 1024) + (double)(cin < 1024 ? cin : 1024));
+  int cps = (int)(48.0e6 / chunk_bytes);                       // ~48 MB of the 126 MB L2 per operand pair
+  const int cps_fill = (int)((long long)wp.n_chunks * base_tiles / (2LL * sms));   // >= 2 tiles per SM overall
+  if (cps > cps_fill) cps = cps_fill;
+  if (cps < 4) cps = 4;
+  if (cps > wp.n_chunks) cps = wp.n_chunks;
+  wp.chunks_per_split = cps;
+  wp.splits = (wp.n_chunks + cps - 1) / cps;
 
   CUtensorMap tmA, tmB;
   auto make = [&](CUtensorMap* m, const float* base, int C) -> int {
@@ -235,5 +253,11 @@ extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, int32
   VNQA_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
   wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, as_stream(stream)>>>(tmA, tmB, wp);
   VNQA_CHECK_CUDA(cudaGetLastError());
+  if (taps != 1) {
+    const long long total_w = (long long)cout * cin * taps;
+    const int blocks = (int)((total_w + 255) / 256 < sms * 8 ? (total_w + 255) / 256 : sms * 8);
+    wgrad_unpack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ws, dw, cout, cin, taps);
+    VNQA_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }

@@ -11,7 +11,7 @@ from ._lib import ConvArgs
 from ._lib import check as _check
 
 IMG_PIX = 130
-_KERNELS_PER_CALL = {"bn_backward": 3, "vnqa_device_check": 0}   # entry points that launch != 1 kernel
+_KERNELS_PER_CALL = {"bn_backward": 3, "vnqa_device_check": 0, "conv_wgrad": 1}   # entry points that launch != 1 kernel
 
 
 def check(rc, what):
@@ -131,8 +131,9 @@ def conv_gemm(w_packed, x, *, taps, cin, cout, n_img, epi, out, flat=False, x_ld
 def conv_wgrad(dy, x, dw, *, n_img, cout, cin, taps, flat=False):
     rows = n_img if flat else n_img * IMG_PIX
     tag = f"conv_wgrad.{'flat' if flat else str(taps) + 'tap'}.k{cin}.n{cout}"
+    ws = torch.zeros(taps, cout, cin, device=dw.device, dtype=torch.float32) if taps != 1 else None
     with _timed(tag, 2.0 * rows * cout * cin * taps):
-        check(_lib.lib().vnqa_conv_wgrad(_p(dy), _p(x), _p(dw), n_img, cout, cin, taps, int(flat), _stream()),
+        check(_lib.lib().vnqa_conv_wgrad(_p(dy), _p(x), _p(dw), _p(ws), n_img, cout, cin, taps, int(flat), _stream()),
               "conv_wgrad")
     return dw
 
