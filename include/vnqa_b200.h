@@ -132,10 +132,12 @@ int vnqa_bn_backward(const float* dx, const float* y, const int32_t* img_frame, 
                      void* stream);
 
 /* ---- FiLM backward (autograd of :229-239): dz = alpha * dout * [alpha z + beta > 0]; dfilm rows get
- * dalpha/dbeta (already masked by the generator's ReLU: zero where alpha/beta == 0); dbias += sum dz. */
+ * dalpha/dbeta; mask_relu != 0 additionally applies the gradient of the FiLM generator's final ReLU (:179), i.e.
+ * zero where alpha/beta == 0 (attention / global-pooling models; the multi-hop model has no such ReLU);
+ * dbias += sum dz. */
 int vnqa_film_backward(const float* dout, const float* z, const float* film, const int32_t* film_row, int32_t film_ld,
                        int32_t alpha_off, int32_t n_img, int32_t C, float* dz, float* dfilm, float* dbias,
-                       void* stream);
+                       int32_t mask_relu, void* stream);
 
 /* out[dst_row[r]][n] = bias[n] + sum_s partial[s][r][n] */
 int vnqa_splitk_reduce(const float* partial, int32_t splits, int32_t rows, int32_t N, const float* bias,
@@ -155,17 +157,39 @@ int vnqa_gp_maxpool_backward(const float* dpooled, const float* pooled, const in
 int vnqa_embed_gates(const int64_t* q_input, const int32_t* q_lens, const float* embed, const float* w_ih,
                      const float* b_ih, const float* b_hh, int32_t B, int32_t L, int32_t E, int32_t H, float* gx,
                      void* stream);
+/* out_states (optional, [n_pass][B][L][H], zero-initialised): every step's output = pad_packed_sequence view used by
+ * the multi-hop model (models/time_multi_hop_pt_stem.py:136-142). */
 int vnqa_lstm_chain_forward(const float* gx, const int32_t* q_lens, const float* whh_t, float* h_state, float* c_state,
                             int32_t n_pass, int32_t B, int32_t L, int32_t H, float* h_pass, float* save_gates,
-                            float* save_c, float* save_hprev, void* stream);
+                            float* save_c, float* save_hprev, float* out_states, void* stream);
+/* dh_pass ([n_pass][B][H]) and/or dh_steps ([n_pass][B][L][H]): incoming gradients; at least one is required. */
 int vnqa_lstm_chain_backward(const float* dh_pass, const int32_t* q_lens, const float* whh, const float* save_gates,
                              const float* save_c, const float* c0, int32_t n_pass, int32_t B, int32_t L, int32_t H,
-                             float* dgates, float* dgx, void* stream);
+                             float* dgates, float* dgx, const float* dh_steps, void* stream);
 /* dembed[q[b][t]][:] += dx[b][t][:] for t < q_len[b]  (dembed pre-initialised by the caller) */
 int vnqa_embed_backward(const int64_t* q_input, const int32_t* q_lens, const float* dx, int32_t B, int32_t L, int32_t E,
                         float* dembed, void* stream);
 int vnqa_embed_gather(const int64_t* q_input, const int32_t* q_lens, const float* embed, int32_t B, int32_t L,
                       int32_t E, float* x, void* stream);
+
+/* ---- K9: multi-hop FiLM decoder of TimeMultiHopFiLMPretrainedStem (models/time_multi_hop_pt_stem.py:124-184):
+ * encoder LayerNorm + NB chained hops of unmasked word attention per frame image; then per hop a Linear (vnqa_sgemm)
+ * and a full-width LayerNorm of which only the block's 2C-wide slice is written to the FiLM matrix. */
+int vnqa_tmh_hops_forward(const float* states, const float* h_last, const int32_t* img_frame, const int32_t* img_clip,
+                          int32_t n_img, int32_t B, int32_t L, int32_t H, int32_t W, int32_t NB, const float* enc_g,
+                          const float* enc_b, const float* w_att, const float* b_att, float* hvec, float* enc_out,
+                          float* enc_stat, float* coefs, void* stream);
+int vnqa_tmh_hops_backward(const float* states, const float* h_last, const int32_t* img_frame, const int32_t* img_clip,
+                           const int32_t* q_lens, int32_t n_img, int32_t B, int32_t L, int32_t H, int32_t W, int32_t NB,
+                           const float* enc_g, const float* w_att, const float* hvec, const float* enc_out,
+                           const float* enc_stat, const float* coefs, const float* dhvec, float* dstates, float* dw_att,
+                           float* db_att, float* denc_g, float* denc_b, void* stream);
+int vnqa_ln_slice_forward(const float* cond, int32_t rows, int32_t N, const float* gamma, const float* beta,
+                          const int32_t* film_row, int32_t film_ld, int32_t off, int32_t width, float* film, float* stat,
+                          void* stream);
+int vnqa_ln_slice_backward(const float* cond, int32_t rows, int32_t N, const float* gamma, const int32_t* film_row,
+                           int32_t film_ld, int32_t off, int32_t width, const float* dfilm, const float* stat,
+                           float* dcond, float* dgamma, float* dbeta, void* stream);
 
 /* ---- K7: temporal attention read-out (:253-295) and its backward */
 int vnqa_attn_tail_forward(const float* feats, const int32_t* v_lens, int32_t n_proc, int32_t B, int32_t T, int32_t A,

@@ -20,12 +20,14 @@ from oracle import film_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["attn_small", "attn_h128", "gp_small"]
+CASES = ["attn_small", "attn_h128", "gp_small", "tmh_small"]
 
 
 def _cls(kind):
-    from videonavqa_b200.models import FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem
-    return {"attn": FiLMAttnPretrainedStem, "gp": FiLMGlobalPoolingPretrainedStem}[kind]
+    from videonavqa_b200.models import (FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem,
+                                        TimeMultiHopFiLMPretrainedStem)
+    return {"attn": FiLMAttnPretrainedStem, "gp": FiLMGlobalPoolingPretrainedStem,
+            "tmh": TimeMultiHopFiLMPretrainedStem}[kind]
 
 
 def build_module(kind, kw, params):
@@ -74,7 +76,11 @@ def test_train_step_matches_reference_and_oracle(name):
     loss = torch.nn.functional.cross_entropy(lo, b["labels"].cuda(), reduction="sum")   # eval.sh:15
     loss.backward()
     ref = torch.from_numpy(z["logits_train"])
-    assert norm_max_err(lo.detach().cpu(), ref) <= 1e-3
+    # tmh_small (32 channels, LayerNorm over 128 values) sits at the edge: the CPU oracle itself moves by 9.6e-4 when
+    # its operands are rounded to tf32, so that case gets 2e-3 against fp32 and is pinned tightly against the
+    # tf32-emulating oracle below; the full-size model is checked at 1e-3 in test_full_size_*.
+    tol = 2e-3 if name == "tmh_small" else 1e-3
+    assert norm_max_err(lo.detach().cpu(), ref) <= tol
     assert abs(loss.item() - float(z["loss_train"])) <= 1e-3 * abs(float(z["loss_train"]))
     # BatchNorm: sequential per-frame EMA with unbiased variance, one "batch" per processed frame (Q6)
     assert int(m.bn_init.num_batches_tracked) == int(z["bn_num_batches_tracked"])
@@ -84,9 +90,10 @@ def test_train_step_matches_reference_and_oracle(name):
     # oracle with the product's operand rounding, same inputs
     C = kw["num_res_block_channels"]
     with O.emulate_tf32():
-        _, _, g_emu, _ = O.loss_and_grads(kind, params, O.new_bn_state(C),
-                                          O.new_film_state(kw["batch_size"], kw["hidden_size"]), b["v"], b["q"],
-                                          b["v_lens"], b["q_lens"], b["labels"], training=True)
+        lo_emu, _, g_emu, _ = O.loss_and_grads(kind, params, O.new_bn_state(C),
+                                               O.new_film_state(kw["batch_size"], kw["hidden_size"]), b["v"], b["q"],
+                                               b["v_lens"], b["q_lens"], b["labels"], training=True)
+    assert norm_max_err(lo.detach().cpu(), lo_emu) <= 3e-4
     named = all_named_params(m)
     worst = 0.0
     for k, gref in grads_ref.items():
@@ -98,7 +105,7 @@ def test_train_step_matches_reference_and_oracle(name):
             continue
         e_emu = rel_l2(g, g_emu[k])
         worst = max(worst, e_emu)
-        if kind == "gp":
+        if kind in ("gp", "tmh"):
             # max-pooling argmax ties re-route whole gradient elements; bound is looser for this model
             assert e_emu <= 2e-2, (k, e_emu)
         else:
@@ -170,6 +177,26 @@ def test_full_size_logits_against_oracle():
         lo = m(v.cuda(), q.cuda(), v_lens.cuda(), q_lens.cuda()).cpu()
         ref, _ = O.film_attn_forward(params, O.new_bn_state(1024), O.new_film_state(B, 128), v, q, v_lens, q_lens,
                                      training=False)
+    assert norm_max_err(lo, ref) <= 1e-3
+    assert (lo.argmax(1) == ref.argmax(1)).all()
+
+
+def test_full_size_multi_hop_logits_against_oracle():
+    """eval.sh multi-hop configuration (C=1024, 3 blocks, 64 tail channels) at B=2, short ragged clips."""
+    from videonavqa_b200.models import TimeMultiHopFiLMPretrainedStem
+    torch.manual_seed(5)
+    B = 2
+    m = TimeMultiHopFiLMPretrainedStem(batch_size=B, q_embedding_size=128, nb_classes=70, num_input_channels=512,
+                                       num_res_block_channels=1024, num_res_blocks=3, num_tail_channels=64,
+                                       hidden_size=128, vocab_size=134).cuda().eval()
+    v, q, _, q_lens, _ = O.synthetic_batch(B, seed=7)
+    v_lens = torch.tensor([6, 3])
+    params = {k: p.detach().cpu() for k, p in all_named_params(m).items()}
+    m.init_hidden()
+    with torch.no_grad():
+        lo = m(v.cuda(), q.cuda(), v_lens.cuda(), q_lens.cuda()).cpu()
+        ref, _ = O.tmh_forward(params, O.new_bn_state(1024), O.new_film_state(B, 128), v, q, v_lens, q_lens,
+                               training=False)
     assert norm_max_err(lo, ref) <= 1e-3
     assert (lo.argmax(1) == ref.argmax(1)).all()
 

@@ -6,9 +6,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from golden_util import load_case, rel_l2, norm_max_err
-from videonavqa_b200.models import FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem
+from videonavqa_b200.models import (FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem,
+                                    TimeMultiHopFiLMPretrainedStem)
 
-CLS = {"attn": FiLMAttnPretrainedStem, "gp": FiLMGlobalPoolingPretrainedStem}
+CLS = {"attn": FiLMAttnPretrainedStem, "gp": FiLMGlobalPoolingPretrainedStem, "tmh": TimeMultiHopFiLMPretrainedStem}
 
 
 def build(kind, kw, params):
@@ -26,7 +27,7 @@ def build(kind, kw, params):
 
 
 def main():
-    names = sys.argv[1:] or ["attn_small", "attn_h128", "gp_small"]
+    names = sys.argv[1:] or ["attn_small", "attn_h128", "gp_small", "tmh_small"]
     for name in names:
         kind, kw, params, grads, b, z = load_case(name)
         m = build(kind, kw, params)

@@ -53,16 +53,20 @@ SIGNATURES = {
     "vnqa_bn_eval_affine": [P, P, P, P, F32, I32, P, P, P],
     "vnqa_bn_apply": [P, P, P, P, P, I32, I32, P],
     "vnqa_bn_backward": [P, P, P, P, I32, P, P, P, I32, I32, P, P, P, P, P, P, P],
-    "vnqa_film_backward": [P, P, P, P, I32, I32, I32, I32, P, P, P, P],
+    "vnqa_film_backward": [P, P, P, P, I32, I32, I32, I32, P, P, P, I32, P],
     "vnqa_splitk_reduce": [P, I32, I32, I32, P, P, P, P],
     "vnqa_gather_rows": [P, P, I32, I32, P, I32, P],
     "vnqa_gp_maxpool": [P, P, I32, I32, I32, P, P, P],
     "vnqa_gp_maxpool_backward": [P, P, P, I32, I32, P, P],
     "vnqa_embed_gates": [P, P, P, P, P, P, I32, I32, I32, I32, P, P],
-    "vnqa_lstm_chain_forward": [P, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P],
-    "vnqa_lstm_chain_backward": [P, P, P, P, P, P, I32, I32, I32, I32, P, P, P],
+    "vnqa_lstm_chain_forward": [P, P, P, P, P, I32, I32, I32, I32, P, P, P, P, P, P],
+    "vnqa_lstm_chain_backward": [P, P, P, P, P, P, I32, I32, I32, I32, P, P, P, P],
     "vnqa_embed_backward": [P, P, P, I32, I32, I32, P, P],
     "vnqa_embed_gather": [P, P, P, I32, I32, I32, P, P],
+    "vnqa_tmh_hops_forward": [P, P, P, P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P],
+    "vnqa_tmh_hops_backward": [P, P, P, P, P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P],
+    "vnqa_ln_slice_forward": [P, I32, I32, P, P, P, I32, I32, I32, P, P, P],
+    "vnqa_ln_slice_backward": [P, I32, I32, P, P, I32, I32, I32, P, P, P, P, P, P],
     "vnqa_attn_tail_forward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "vnqa_attn_tail_backward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
 }

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(4 * H, 1)
 lstm_chain_fwd_kernel(const float* __restrict__ gx, const int* __restrict__ q_lens, const float* __restrict__ whh_t,
                       float* __restrict__ h_state, float* __restrict__ c_state, int n_pass, int B, int L,
                       float* __restrict__ h_pass, float* __restrict__ save_gates, float* __restrict__ save_c,
-                      float* __restrict__ save_h) {
+                      float* __restrict__ save_h, float* __restrict__ out_states) {
   constexpr int H4 = 4 * H;
   constexpr int KR = H - KS;  // rows kept in registers
   extern __shared__ float sm[];
@@ -91,6 +91,7 @@ lstm_chain_fwd_kernel(const float* __restrict__ gx, const int* __restrict__ q_le
         const float h = og * tanhf(c);
         const float h_prev = hs[j];
         hs[j] = h;
+        if (out_states) out_states[(((long long)p * B + b) * L + t) * H + j] = h;   // pad_packed_sequence view
         if (save_gates) {
           const long long s = ((long long)p * B + b) * L + t;
           save_gates[s * H4 + j] = ig;
@@ -119,7 +120,9 @@ __global__ void __launch_bounds__(4 * H, 1)
 lstm_chain_bwd_kernel(const float* __restrict__ dh_pass, const int* __restrict__ q_lens, const float* __restrict__ whh,
                       const float* __restrict__ save_gates, const float* __restrict__ save_c,
                       const float* __restrict__ c0, int n_pass, int B, int L, float* __restrict__ dgates,
-                      float* __restrict__ dgx) {
+                      float* __restrict__ dgx, const float* __restrict__ dh_steps) {
+  // dh_steps (optional, [n_pass][B][L][H]): gradient arriving at the OUTPUT of every step (multi-hop model, where
+  // all word states are consumed); dh_pass (optional): gradient at the state after each pass.
   constexpr int H4 = 4 * H;
   constexpr int KR = H - KS;
   extern __shared__ float sm[];
@@ -141,10 +144,11 @@ lstm_chain_bwd_kernel(const float* __restrict__ dh_pass, const int* __restrict__
   const int ql = q_lens[b];
   float dh = 0.f, dc = 0.f;  // threads tid < H hold the running state gradients
   for (int p = n_pass - 1; p >= 0; --p) {
-    if (tid < H) dh += dh_pass[((long long)p * B + b) * H + tid];
+    if (tid < H && dh_pass) dh += dh_pass[((long long)p * B + b) * H + tid];
     for (int t = ql - 1; t >= 0; --t) {
       const long long s = ((long long)p * B + b) * L + t;
       if (tid < H) {
+        if (dh_steps) dh += dh_steps[s * H + tid];
         const float ig = save_gates[s * H4 + tid], fg = save_gates[s * H4 + H + tid],
                     gg = save_gates[s * H4 + 2 * H + tid], og = save_gates[s * H4 + 3 * H + tid];
         const float cc = save_c[s * H + tid];
@@ -182,21 +186,22 @@ lstm_chain_bwd_kernel(const float* __restrict__ dh_pass, const int* __restrict__
 
 template <int H, int KS>
 static int launch_fwd(const float* gx, const int* q_lens, const float* whh_t, float* h_state, float* c_state, int n_pass,
-                      int B, int L, float* h_pass, float* sg, float* sc, float* sh, cudaStream_t st) {
+                      int B, int L, float* h_pass, float* sg, float* sc, float* sh, float* states, cudaStream_t st) {
   auto kern = lstm_chain_fwd_kernel<H, KS>;
   const int smem = (KS * 4 * H + H + 4 * H) * 4;
   VNQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<B, 4 * H, smem, st>>>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, sg, sc, sh);
+  kern<<<B, 4 * H, smem, st>>>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, sg, sc, sh, states);
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 template <int H, int KS>
 static int launch_bwd(const float* dh_pass, const int* q_lens, const float* whh, const float* sg, const float* sc,
-                      const float* c0, int n_pass, int B, int L, float* dgates, float* dgx, cudaStream_t st) {
+                      const float* c0, int n_pass, int B, int L, float* dgates, float* dgx, const float* dh_steps,
+                      cudaStream_t st) {
   auto kern = lstm_chain_bwd_kernel<H, KS>;
   const int smem = (KS * 4 * H + 4 * H + 4 * H) * 4;
   VNQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<B, 4 * H, smem, st>>>(dh_pass, q_lens, whh, sg, sc, c0, n_pass, B, L, dgates, dgx);
+  kern<<<B, 4 * H, smem, st>>>(dh_pass, q_lens, whh, sg, sc, c0, n_pass, B, L, dgates, dgx, dh_steps);
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -234,26 +239,27 @@ extern "C" int vnqa_embed_backward(const int64_t* q_input, const int32_t* q_lens
 
 extern "C" int vnqa_lstm_chain_forward(const float* gx, const int32_t* q_lens, const float* whh_t, float* h_state,
                                        float* c_state, int32_t n_pass, int32_t B, int32_t L, int32_t H, float* h_pass,
-                                       float* save_gates, float* save_c, float* save_h, void* stream) {
+                                       float* save_gates, float* save_c, float* save_h, float* out_states, void* stream) {
   VNQA_REQUIRE(gx && q_lens && whh_t && h_state && c_state && h_pass, "vnqa_lstm_chain_forward: null pointer");
   cudaStream_t st = as_stream(stream);
   switch (H) {
-    case 32: return launch_fwd<32, 32>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, save_gates, save_c, save_h, st);
-    case 64: return launch_fwd<64, 64>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, save_gates, save_c, save_h, st);
-    case 128: return launch_fwd<128, 96>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, save_gates, save_c, save_h, st);
+    case 32: return launch_fwd<32, 32>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, save_gates, save_c, save_h, out_states, st);
+    case 64: return launch_fwd<64, 64>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, save_gates, save_c, save_h, out_states, st);
+    case 128: return launch_fwd<128, 96>(gx, q_lens, whh_t, h_state, c_state, n_pass, B, L, h_pass, save_gates, save_c, save_h, out_states, st);
     default: set_error("vnqa_lstm_chain_forward: hidden size %d not supported (32, 64, 128)", H); return -1;
   }
 }
 
 extern "C" int vnqa_lstm_chain_backward(const float* dh_pass, const int32_t* q_lens, const float* whh,
                                         const float* save_gates, const float* save_c, const float* c0, int32_t n_pass,
-                                        int32_t B, int32_t L, int32_t H, float* dgates, float* dgx, void* stream) {
-  VNQA_REQUIRE(dh_pass && q_lens && whh && save_gates && save_c && c0 && dgates && dgx, "vnqa_lstm_chain_backward: null");
+                                        int32_t B, int32_t L, int32_t H, float* dgates, float* dgx, const float* dh_steps,
+                                        void* stream) {
+  VNQA_REQUIRE((dh_pass || dh_steps) && q_lens && whh && save_gates && save_c && c0 && dgates && dgx, "vnqa_lstm_chain_backward: null");
   cudaStream_t st = as_stream(stream);
   switch (H) {
-    case 32: return launch_bwd<32, 32>(dh_pass, q_lens, whh, save_gates, save_c, c0, n_pass, B, L, dgates, dgx, st);
-    case 64: return launch_bwd<64, 64>(dh_pass, q_lens, whh, save_gates, save_c, c0, n_pass, B, L, dgates, dgx, st);
-    case 128: return launch_bwd<128, 96>(dh_pass, q_lens, whh, save_gates, save_c, c0, n_pass, B, L, dgates, dgx, st);
+    case 32: return launch_bwd<32, 32>(dh_pass, q_lens, whh, save_gates, save_c, c0, n_pass, B, L, dgates, dgx, dh_steps, st);
+    case 64: return launch_bwd<64, 64>(dh_pass, q_lens, whh, save_gates, save_c, c0, n_pass, B, L, dgates, dgx, dh_steps, st);
+    case 128: return launch_bwd<128, 96>(dh_pass, q_lens, whh, save_gates, save_c, c0, n_pass, B, L, dgates, dgx, dh_steps, st);
     default: set_error("vnqa_lstm_chain_backward: hidden size %d not supported (32, 64, 128)", H); return -1;
   }
 }

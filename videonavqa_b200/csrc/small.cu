@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(128) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int C,
                                                             float* __restrict__ s1, float* __restrict__ s2) {
-  const int img = blockIdx.x;
-  const int c = blockIdx.y * 128 + threadIdx.x;
+  const int img = blockIdx.y;                     // channel slab is the fastest grid index: co-scheduled blocks
+  const int c = blockIdx.x * 128 + threadIdx.x;   // sweep whole pixel rows (full DRAM pages)
   if (c >= C) return;
   const int f = img_frame[img];
   const float m = mean[(long long)f * C + c], r = rstd[(long long)f * C + c];
@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(128) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ s1, const float* __restrict__ s2,
                                                            int C, float* __restrict__ dy, float* __restrict__ dbias) {
-  const int img = blockIdx.x;
-  const int c = blockIdx.y * 128 + threadIdx.x;
+  const int img = blockIdx.y;
+  const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= C) return;
   const int f = img_frame[img];
   const float inv_n = 1.f / ((float)frame_ct[f] * VNQA_IMG_PIX);
@@ -200,34 +200,59 @@ __global__ void bn_bwd_params_kernel(const float* __restrict__ s1, const float* 
 // Given dOut (gradient of relu(alpha*z+beta)+res wrt the FiLM branch), saved z and the FiLM rows:
 //   dF = dOut * [alpha*z+beta > 0]; dz = alpha*dF; dalpha[img][c] = sum_pix dF*z; dbeta[img][c] = sum_pix dF;
 //   dbias[c] += sum dz.  Autograd of models/film_attn_pt_stem.py:229-239.  One block per (image, 128-ch slab).
-__global__ void __launch_bounds__(128) film_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z,
+__global__ void __launch_bounds__(256) film_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z,
                                                        const float* __restrict__ film,
                                                        const int* __restrict__ film_row, int film_ld, int alpha_off,
                                                        int C, float* __restrict__ dz, float* __restrict__ dfilm,
-                                                       float* __restrict__ dbias) {
+                                                       float* __restrict__ dbias, int mask_relu) {
+  // one block per image; a thread owns 4 consecutive channels (float4), so a warp step reads 512 contiguous bytes and
+  // the block sweeps whole 4*C-byte pixel rows: full DRAM pages, 16-byte transactions
   const int img = blockIdx.x;
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= C) return;
+  const int C4 = C >> 2;
   const long long frow = (long long)film_row[img] * film_ld + alpha_off;
-  const float alpha = film[frow + c], beta = film[frow + C + c];
-  const long long base = (long long)img * VNQA_IMG_PIX * C + c;
-  float da = 0.f, db = 0.f, dzs = 0.f;
-#pragma unroll 10
-  for (int p = 0; p < VNQA_IMG_PIX; ++p) {
-    const long long i = base + (long long)p * C;
-    const float zz = __ldg(z + i);
-    const float d = fmaf(alpha, zz, beta) > 0.f ? __ldg(dout + i) : 0.f;
-    da = fmaf(d, zz, da);
-    db += d;
-    const float dzv = tf32_round(alpha * d);
-    dz[i] = dzv;
-    dzs += dzv;
+  for (int q = threadIdx.x; q < C4; q += blockDim.x) {
+    const float4 al = *reinterpret_cast<const float4*>(film + frow + 4 * q);
+    const float4 be = *reinterpret_cast<const float4*>(film + frow + C + 4 * q);
+    const float4* zp = reinterpret_cast<const float4*>(z + (long long)img * VNQA_IMG_PIX * C) + q;
+    const float4* dp = reinterpret_cast<const float4*>(dout + (long long)img * VNQA_IMG_PIX * C) + q;
+    float4* op = reinterpret_cast<float4*>(dz + (long long)img * VNQA_IMG_PIX * C) + q;
+    float4 da = make_float4(0.f, 0.f, 0.f, 0.f), db = da, ds = da;
+#pragma unroll 5
+    for (int p = 0; p < VNQA_IMG_PIX; ++p) {
+      const float4 zz = __ldg(zp + (long long)p * C4);
+      const float4 dd = __ldg(dp + (long long)p * C4);
+      float4 o;
+      {
+        const float d = fmaf(al.x, zz.x, be.x) > 0.f ? dd.x : 0.f;
+        da.x = fmaf(d, zz.x, da.x); db.x += d; o.x = tf32_round(al.x * d); ds.x += o.x;
+      }
+      {
+        const float d = fmaf(al.y, zz.y, be.y) > 0.f ? dd.y : 0.f;
+        da.y = fmaf(d, zz.y, da.y); db.y += d; o.y = tf32_round(al.y * d); ds.y += o.y;
+      }
+      {
+        const float d = fmaf(al.z, zz.z, be.z) > 0.f ? dd.z : 0.f;
+        da.z = fmaf(d, zz.z, da.z); db.z += d; o.z = tf32_round(al.z * d); ds.z += o.z;
+      }
+      {
+        const float d = fmaf(al.w, zz.w, be.w) > 0.f ? dd.w : 0.f;
+        da.w = fmaf(d, zz.w, da.w); db.w += d; o.w = tf32_round(al.w * d); ds.w += o.w;
+      }
+      op[(long long)p * C4] = o;
+    }
+    // each (film row, channel) is owned by exactly one image: plain stores.  When the FiLM generator ends in a ReLU
+    // (:179, mask_relu) its gradient is masked where the output is 0
+#define KEEP(v) (!mask_relu || (v) > 0.f)
+    *reinterpret_cast<float4*>(dfilm + frow + 4 * q) =
+        make_float4(KEEP(al.x) ? da.x : 0.f, KEEP(al.y) ? da.y : 0.f, KEEP(al.z) ? da.z : 0.f, KEEP(al.w) ? da.w : 0.f);
+    *reinterpret_cast<float4*>(dfilm + frow + C + 4 * q) =
+        make_float4(KEEP(be.x) ? db.x : 0.f, KEEP(be.y) ? db.y : 0.f, KEEP(be.z) ? db.z : 0.f, KEEP(be.w) ? db.w : 0.f);
+#undef KEEP
+    atomicAdd(dbias + 4 * q + 0, ds.x);
+    atomicAdd(dbias + 4 * q + 1, ds.y);
+    atomicAdd(dbias + 4 * q + 2, ds.z);
+    atomicAdd(dbias + 4 * q + 3, ds.w);
   }
-  // each (film row, channel) is owned by exactly one image: plain stores
-  // ... and the FiLM generator ends in a ReLU (:179): its gradient is masked where the output is 0
-  dfilm[frow + c] = alpha > 0.f ? da : 0.f;
-  dfilm[frow + C + c] = beta > 0.f ? db : 0.f;
-  atomicAdd(dbias + c, dzs);
 }
 
 // ------------------------------------------------------------------------------------------------ misc
@@ -389,7 +414,7 @@ extern "C" int vnqa_bn_backward(const float* dx, const float* y, const int32_t* 
   cudaStream_t st = as_stream(stream);
   VNQA_CHECK_CUDA(cudaMemsetAsync(s1, 0, (size_t)n_frames * C * 4, st));
   VNQA_CHECK_CUDA(cudaMemsetAsync(s2, 0, (size_t)n_frames * C * 4, st));
-  dim3 grid(n_img, (C + 127) / 128);
+  dim3 grid((C + 127) / 128, n_img);
   bn_bwd_reduce_kernel<<<grid, 128, 0, st>>>(dx, y, img_frame, mean, rstd, C, s1, s2);
   bn_bwd_apply_kernel<<<grid, 128, 0, st>>>(dx, y, img_frame, frame_ct, mean, rstd, gamma, s1, s2, C, dy, dbias);
   bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(s1, s2, n_frames, C, dgamma, dbeta);
@@ -399,11 +424,12 @@ extern "C" int vnqa_bn_backward(const float* dx, const float* y, const int32_t* 
 
 extern "C" int vnqa_film_backward(const float* dout, const float* z, const float* film, const int32_t* film_row,
                                   int32_t film_ld, int32_t alpha_off, int32_t n_img, int32_t C, float* dz, float* dfilm,
-                                  float* dbias, void* stream) {
+                                  float* dbias, int32_t mask_relu, void* stream) {
   VNQA_REQUIRE(dout && z && film && film_row && dz && dfilm && dbias, "vnqa_film_backward: null");
-  dim3 grid(n_img, (C + 127) / 128);
-  film_bwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(dout, z, film, film_row, film_ld, alpha_off, C, dz, dfilm,
-                                                       dbias);
+  VNQA_REQUIRE(C % 4 == 0 && film_ld % 4 == 0 && alpha_off % 4 == 0, "vnqa_film_backward: C/film_ld/alpha_off must be multiples of 4");
+  const int threads = C / 4 >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
+  film_bwd_kernel<<<n_img, threads, 0, as_stream(stream)>>>(dout, z, film, film_row, film_ld, alpha_off, C, dz, dfilm,
+                                                            dbias, mask_relu);
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -52,7 +52,7 @@ class Plan:
         film_row = img_frame * B + img_clip       # row of the (n_frames*B, 2*C*NB) FiLM matrix
         feat_row = img_clip * T + img_frame       # row of the (B*T, A) attention feature matrix
         packed = np.concatenate([img_of.reshape(-1), img_frame, film_row, feat_row, frame_ct,
-                                 v.astype(np.int32)]).astype(np.int32)
+                                 v.astype(np.int32), img_clip]).astype(np.int32)
         dev = torch.from_numpy(packed)
         if torch.device(device).type == "cuda":
             dev = dev.pin_memory().to(device, non_blocking=True)
@@ -62,7 +62,8 @@ class Plan:
         self.film_row = dev[o:o + self.n_img]; o += self.n_img
         self.feat_row = dev[o:o + self.n_img]; o += self.n_img
         self.frame_ct = dev[o:o + self.n_frames]; o += self.n_frames
-        self.v_lens32 = dev[o:o + B]
+        self.v_lens32 = dev[o:o + B]; o += B
+        self.img_clip = dev[o:o + self.n_img]
         self.frame_ct_host = frame_ct
 
 
@@ -106,8 +107,36 @@ def _choose_splits(n_img, k_total):
 
 
 # ======================================================================================== trunk forward
-def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save, enc_prefix="film_layer.0.",
-                  film_lin_prefix="film_layer.1."):
+def lstm_generator_forward(P, cache, plan, q_input, q_lens32, film_h, film_c, save, nb, C):
+    """FiLM generator of the attention / global-pooling models (compute_film_values, film_attn_pt_stem.py:144-181):
+    chained question LSTM -> Linear -> ReLU.  Returns (film matrix, generator context)."""
+    enc, lin = "film_layer.0.", "film_layer.1."
+    B = plan.B
+    gx = ops.embed_gates(q_input, q_lens32, P["embed.weight"], P[enc + "weight_ih_l0"], P[enc + "bias_ih_l0"],
+                         P[enc + "bias_hh_l0"])
+    whh_t = cache.get(enc + "whh_t", P[enc + "weight_hh_l0"], lambda w: w.t().contiguous())
+    c0 = film_c.clone() if save else None
+    h_pass, sg, sc, sh = ops.lstm_chain_forward(gx, q_lens32, whh_t, film_h, film_c, plan.n_frames, save=save)
+    H = h_pass.shape[-1]
+    film = ops.linear(h_pass.view(plan.n_frames * B, H), P[lin + "weight"], P[lin + "bias"], relu=True)
+    return film, dict(h_pass=h_pass, gx=gx, sg=sg, sc=sc, sh=sh, c0=c0, enc_prefix=enc, film_lin_prefix=lin)
+
+
+def lstm_generator_backward(P, cache, ctx, dfilm, q_input, q_lens32, sink):
+    """Backward of lstm_generator_forward (the ReLU mask was already applied by film_backward)."""
+    plan = ctx["plan"]
+    enc, lin = ctx["enc_prefix"], ctx["film_lin_prefix"]
+    h_pass = ctx["h_pass"]
+    H = h_pass.shape[-1]
+    hp2 = h_pass.view(plan.n_frames * plan.B, H)
+    sink[lin + "weight"] = ops.linear_wgrad(dfilm, hp2)
+    sink[lin + "bias"] = ops.colsum(dfilm)
+    dh_pass = ops.linear_dgrad(dfilm, P[lin + "weight"])
+    question_backward(P, ctx, dh_pass, q_input, q_lens32, sink, enc)
+
+
+def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save,
+                  gen_fwd=lstm_generator_forward):
     """conv_init+ReLU+BN, question encoder + FiLM generator, FiLM ResBlocks.  Returns (x_last, ctx)."""
     dev = v_input.device
     B, c_in = v_input.shape[0], v_input.shape[1]
@@ -126,18 +155,11 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
     side = _side_stream(dev)
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        w_ih, w_hh = P[enc_prefix + "weight_ih_l0"], P[enc_prefix + "weight_hh_l0"]
-        gx = ops.embed_gates(q_input, q_lens32, P["embed.weight"], w_ih, P[enc_prefix + "bias_ih_l0"],
-                             P[enc_prefix + "bias_hh_l0"])
-        whh_t = cache.get(enc_prefix + "whh_t", w_hh, lambda w: w.t().contiguous())
-        c0 = film_c.clone() if save else None
-        h_pass, sg, sc, sh = ops.lstm_chain_forward(gx, q_lens32, whh_t, film_h, film_c, plan.n_frames, save=save)
-        H = h_pass.shape[-1]
-        film = ops.linear(h_pass.view(plan.n_frames * B, H), P[film_lin_prefix + "weight"], P[film_lin_prefix + "bias"],
-                          relu=True)
-        for t in (gx, h_pass, film, sg, sc, sh, c0):
-            if t is not None:
-                t.record_stream(main)   # allocated on the side stream, consumed on the main stream
+        film, gctx = gen_fwd(P, cache, plan, q_input, q_lens32, film_h, film_c, save, nb, C)
+        film.record_stream(main)        # allocated on the side stream, consumed on the main stream
+        for t in gctx.values():
+            if torch.is_tensor(t):
+                t.record_stream(main)
     film_ready = torch.cuda.Event()
     film_ready.record(side)
 
@@ -182,8 +204,8 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
     if nb == 0:
         main.wait_event(film_ready)
     if save:
-        ctx.update(x0=x0, xs=xs, ress=ress, zs=zs, film=film, h_pass=h_pass, gx=gx, sg=sg, sc=sc, sh=sh, c0=c0,
-                   enc_prefix=enc_prefix, film_lin_prefix=film_lin_prefix)
+        ctx.update(x0=x0, xs=xs, ress=ress, zs=zs, film=film)
+        ctx.update(gctx)
     return x, ctx
 
 
@@ -198,18 +220,41 @@ def _side_stream(dev):
 
 
 # ======================================================================================== trunk backward
-def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads):
-    """Backward of trunk_forward given d(loss)/d(x_last); fills `grads` (name -> tensor)."""
+def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lstm_generator_backward, mask_relu=True):
+    """Backward of trunk_forward given d(loss)/d(x_last); fills `grads` (name -> tensor).  mask_relu: the FiLM
+    generator ends in a ReLU (attention / global-pooling models)."""
     plan, C, nb, c_in = ctx["plan"], ctx["C"], ctx["nb"], ctx["c_in"]
     n_img, B = plan.n_img, plan.B
     dev = dx_last.device
     film = ctx["film"]
     dfilm = torch.zeros_like(film)
     dout = dx_last
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    gen_done = None
+
+    def generator_backward():
+        """FiLM generator backward (+ chained-LSTM BPTT + embedding).  Latency-bound and independent of the remaining
+        convolution backward: runs on the side stream as soon as dfilm is complete (after block 0's FiLM backward)."""
+        nonlocal gen_done
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            local = GradSink(None)
+            gen_bwd(P, cache, ctx, dfilm, q_input, q_lens32, local)
+            for t in local.values():
+                t.record_stream(main)
+            dfilm.record_stream(side)
+            gen_done = (torch.cuda.Event(), local)
+            gen_done[0].record(side)
+
+    if nb == 0:
+        generator_backward()
     for k in reversed(range(nb)):
         res, z, x_in = ctx["ress"][k], ctx["zs"][k], ctx["xs"][k]
         db3 = torch.zeros(C, device=dev, dtype=torch.float32)
-        dz = ops.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3)
+        dz = ops.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3, mask_relu=mask_relu)
+        if k == 0:
+            generator_backward()
         grads[f"film_pipeline.{k}.bias"] = db3
         dw3 = torch.zeros_like(P[f"film_pipeline.{k}.weight"])
         ops.conv_wgrad(dz, res, dw3, n_img=n_img, cout=C, cin=C, taps=9)
@@ -241,23 +286,20 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads):
     dw0 = torch.zeros_like(P["conv_init.weight"])
     ops.conv_wgrad(dy0, ctx["x0"], dw0, n_img=n_img, cout=C, cin=c_in, taps=9)
     grads["conv_init.weight"] = dw0
-    # ---- FiLM generator: Linear+ReLU (mask already applied by film_backward) and the chained LSTM
-    enc, lin = ctx["enc_prefix"], ctx["film_lin_prefix"]
-    h_pass = ctx["h_pass"]
-    H = h_pass.shape[-1]
-    hp2 = h_pass.view(plan.n_frames * B, H)
-    grads[lin + "weight"] = ops.linear_wgrad(dfilm, hp2)
-    grads[lin + "bias"] = ops.colsum(dfilm)
-    dh_pass = ops.linear_dgrad(dfilm, P[lin + "weight"])
-    question_backward(P, ctx, dh_pass, q_input, q_lens32, grads, enc)
+    # ---- join the side stream; its gradients are published (and all-reduced, if a hook is set) from the main stream
+    main.wait_event(gen_done[0])
+    for n_, t_ in gen_done[1].items():
+        grads[n_] = t_
 
 
-def question_backward(P, ctx, dh_pass, q_input, q_lens32, grads, enc):
-    """BPTT through the chained question LSTM + embedding (autograd of compute_film_values, :144-171)."""
+def question_backward(P, ctx, dh_pass, q_input, q_lens32, grads, enc, dh_steps=None):
+    """BPTT through the chained question LSTM + embedding (autograd of compute_film_values, :144-171).
+    dh_pass: gradient at the state after each pass; dh_steps: gradient at every step output (multi-hop model)."""
     sg, sc, sh = ctx["sg"], ctx["sc"], ctx["sh"]
     n_pass, B, L, H4 = sg.shape
     H = H4 // 4
-    dgates, dgx = ops.lstm_chain_backward(dh_pass, q_lens32, P[enc + "weight_hh_l0"], sg, sc, ctx["c0"])
+    dgates, dgx = ops.lstm_chain_backward(dh_pass, q_lens32, P[enc + "weight_hh_l0"], sg, sc, ctx["c0"],
+                                          dh_steps=dh_steps)
     steps = n_pass * B * L
     grads[enc + "weight_hh_l0"] = ops.linear_wgrad(dgates.view(steps, H4), sh.view(steps, H), ksplit=64)
     dgx2 = dgx.view(B * L, H4)
@@ -356,6 +398,12 @@ def gp_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, fi
     B, T = v_input.shape[0], v_input.shape[-1]
     plan = Plan(v_lens_host, B, T, dev)
     x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
+    return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
+
+
+def _gp_tail_forward(P, cache, plan, x, ctx, B, T, save):
+    """relu(c1x1_tail) -> max over frames -> Linear (models/film_global_pooling_pt_stem.py:228-238)."""
+    dev = x.device
     C, n_img = ctx["C"], plan.n_img
     tail = P["c1x1_tail.weight"].shape[0]
     wt = cache.get("c1x1_tail", P["c1x1_tail.weight"], ops.pack_conv_weight)
@@ -370,10 +418,15 @@ def gp_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, fi
 
 
 def gp_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+    grads = GradSink(grad_hook)
+    dx_last = _gp_tail_backward(P, ctx, dlogits, grads)
+    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
+    return grads
+
+
+def _gp_tail_backward(P, ctx, dlogits, grads):
     plan, C, tail = ctx["plan"], ctx["C"], ctx["tail"]
     B, n_img = plan.B, plan.n_img
-    dev = dlogits.device
-    grads = GradSink(grad_hook)
     dlogits = dlogits.contiguous()
     pooled = ctx["pooled"]
     grads["out_linear.weight"] = ops.linear_wgrad(dlogits, pooled)
@@ -385,6 +438,90 @@ def gp_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
     x_last = ctx["x_last"]
     # tail conv gradients: tail is tiny (<= 64 channels) -> fp32 SGEMMs
     grads["c1x1_tail.weight"] = ops.linear_wgrad(dy2, x_last.view(n_img * IMG_PIX, C), ksplit=32).view(tail, C, 1, 1)
-    dx_last = ops.linear_dgrad(dy2, P["c1x1_tail.weight"].view(tail, C)).view(n_img, IMG_PIX, C)
-    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
+    return ops.linear_dgrad(dy2, P["c1x1_tail.weight"].view(tail, C)).view(n_img, IMG_PIX, C)
+
+
+# ======================================================================================== multi-hop model
+def tmh_generator_forward(P, cache, plan, q_input, q_lens32, film_h, film_c, save, nb, C):
+    """compute_film_encoding + decode_to_film_values of TimeMultiHopFiLMPretrainedStem
+    (models/time_multi_hop_pt_stem.py:124-184) for every frame image at once."""
+    enc = "q_encoder."
+    B = plan.B
+    gx = ops.embed_gates(q_input, q_lens32, P["embed.weight"], P[enc + "weight_ih_l0"], P[enc + "bias_ih_l0"],
+                         P[enc + "bias_hh_l0"])
+    whh_t = cache.get(enc + "whh_t", P[enc + "weight_hh_l0"], lambda w: w.t().contiguous())
+    c0 = film_c.clone() if save else None
+    h_pass, sg, sc, sh, states = ops.lstm_chain_forward(gx, q_lens32, whh_t, film_h, film_c, plan.n_frames, save=save,
+                                                        want_states=True)
+    W = plan.max_q_len                       # pad_packed_sequence pads to the longest question of the batch (:136)
+    hvec, enc_out, enc_stat, coefs = ops.tmh_hops_forward(
+        states, h_pass, plan.img_frame, plan.img_clip, W, nb, P["encoder_norm.weight"], P["encoder_norm.bias"],
+        P["fc_hidden_attn.weight"], P["fc_hidden_attn.bias"])
+    N = 2 * C * nb
+    film = torch.zeros(plan.n_frames * B, N, device=gx.device, dtype=torch.float32)
+    conds, stats = [], []
+    for k in range(nb):
+        cond = ops.linear(hvec[k], P["fc_attn_out.weight"], P["fc_attn_out.bias"])        # full width, every hop (Q10)
+        stat = ops.ln_slice_forward(cond, P["decoder_norm.weight"], P["decoder_norm.bias"], plan.film_row, film,
+                                    2 * k * C, 2 * C)
+        if save:
+            conds.append(cond); stats.append(stat)
+    g = dict(h_pass=h_pass, gx=gx, sg=sg, sc=sc, sh=sh, c0=c0, enc_prefix=enc)
+    if save:
+        g.update(states=states, hvec=hvec, enc_out=enc_out, enc_stat=enc_stat, coefs=coefs, W=W,
+                 conds=torch.stack(conds), ln_stats=torch.stack(stats))
+    return film, g
+
+
+def tmh_generator_backward(P, cache, ctx, dfilm, q_input, q_lens32, sink):
+    plan, C, nb = ctx["plan"], ctx["C"], ctx["nb"]
+    dev = dfilm.device
+    hvec, W = ctx["hvec"], ctx["W"]
+    H = hvec.shape[-1]
+    N = 2 * C * nb
+    dgam = torch.zeros(N, device=dev, dtype=torch.float32)
+    dbet = torch.zeros(N, device=dev, dtype=torch.float32)
+    dw_out = torch.zeros_like(P["fc_attn_out.weight"])
+    db_out = torch.zeros(N, device=dev, dtype=torch.float32)
+    dhvec = torch.empty_like(hvec)
+    for k in range(nb):
+        dcond = ops.ln_slice_backward(ctx["conds"][k], P["decoder_norm.weight"], plan.film_row, dfilm, 2 * k * C, 2 * C,
+                                      ctx["ln_stats"][k], dgam, dbet)
+        ops.linear_wgrad(dcond, hvec[k], out=dw_out)         # accumulated over the hops
+        ops.colsum(dcond, out=db_out)
+        dhvec[k].copy_(ops.linear_dgrad(dcond, P["fc_attn_out.weight"]))
+    sink["decoder_norm.weight"] = dgam
+    sink["decoder_norm.bias"] = dbet
+    sink["fc_attn_out.weight"] = dw_out
+    sink["fc_attn_out.bias"] = db_out
+    dw_att = torch.zeros_like(P["fc_hidden_attn.weight"])
+    db_att = torch.zeros_like(P["fc_hidden_attn.bias"])
+    deg = torch.zeros(H, device=dev, dtype=torch.float32)
+    deb = torch.zeros(H, device=dev, dtype=torch.float32)
+    dstates = ops.tmh_hops_backward(ctx["states"], ctx["h_pass"], plan.img_frame, plan.img_clip, q_lens32, W, nb,
+                                    P["encoder_norm.weight"], P["fc_hidden_attn.weight"], hvec, ctx["enc_out"],
+                                    ctx["enc_stat"], ctx["coefs"], dhvec, dw_att, db_att, deg, deb)
+    sink["fc_hidden_attn.weight"] = dw_att
+    sink["fc_hidden_attn.bias"] = db_att
+    sink["encoder_norm.weight"] = deg
+    sink["encoder_norm.bias"] = deb
+    question_backward(P, ctx, None, q_input, q_lens32, sink, ctx["enc_prefix"], dh_steps=dstates)
+
+
+def tmh_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens_host, q_lens32, film_h, film_c, training, save):
+    """TimeMultiHopFiLMPretrainedStem.forward (models/time_multi_hop_pt_stem.py:191-250): conv trunk with the
+    multi-hop FiLM generator, then the global-pooling tail."""
+    dev = v_input.device
+    B, T = v_input.shape[0], v_input.shape[-1]
+    plan = Plan(v_lens_host, B, T, dev)
+    plan.max_q_len = int(max(q_lens_host))
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save,
+                           gen_fwd=tmh_generator_forward)
+    return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
+
+
+def tmh_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+    grads = GradSink(grad_hook)
+    dx_last = _gp_tail_backward(P, ctx, dlogits, grads)
+    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=tmh_generator_backward, mask_relu=False)
     return grads

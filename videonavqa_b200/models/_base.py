@@ -108,6 +108,7 @@ class FilmModuleBase(nn.Module):
         L = q_input.shape[1]
         if min(q_host) < 1 or max(q_host) > L:
             raise ValueError(f"q_lens must lie in [1, {L}]")
+        self._last_q_host = q_host
         q_lens_dev = q_lens.to(dev).long()
         q_lens32 = q_lens_dev.to(torch.int32)
         # film_hidden is kept in q_len-sorted order like the reference (film_attn_pt_stem.py:153-160)

@@ -163,18 +163,20 @@ def linear_dgrad(dy, w):
     return sgemm(dy, w, M=M, N=K, K=N, a_strides=(dy.stride(0), dy.stride(1)), b_strides=(w.stride(1), w.stride(0)))
 
 
-def linear_wgrad(dy, x, ksplit=1):
-    """dy (M,N)^T @ x (M,K) -> (N,K)."""
+def linear_wgrad(dy, x, ksplit=1, out=None):
+    """dy (M,N)^T @ x (M,K) -> (N,K); with `out` the product is accumulated onto it."""
     M, N = dy.shape
     K = x.shape[1]
     return sgemm(dy, x, M=N, N=K, K=M, a_strides=(dy.stride(1), dy.stride(0)), b_strides=(x.stride(1), x.stride(0)),
-                 ksplit=ksplit)
+                 ksplit=ksplit, out=out, accumulate=out is not None)
 
 
-def colsum(x):
+def colsum(x, out=None):
     rows, n = x.shape
-    out = torch.empty(n, device=x.device, dtype=torch.float32)
-    check(_lib.lib().vnqa_colsum(_p(x), rows, n, x.stride(0), _p(out), 0, _stream()), "colsum")
+    acc = out is not None
+    if out is None:
+        out = torch.empty(n, device=x.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_colsum(_p(x), rows, n, x.stride(0), _p(out), int(acc), _stream()), "colsum")
     return out
 
 
@@ -215,11 +217,11 @@ def bn_backward(dx, y, img_frame, frame_ct, n_frames, mean, rstd, gamma, dbias, 
     return dy
 
 
-def film_backward(dout, z, film, film_row, alpha_off, dfilm, dbias):
+def film_backward(dout, z, film, film_row, alpha_off, dfilm, dbias, mask_relu=True):
     n_img, _, C = z.shape
     dz = torch.empty_like(z)
     check(_lib.lib().vnqa_film_backward(_p(dout), _p(z), _p(film), _p(film_row), film.stride(0), alpha_off, n_img, C,
-                                        _p(dz), _p(dfilm), _p(dbias), _stream()), "film_backward")
+                                        _p(dz), _p(dfilm), _p(dbias), int(mask_relu), _stream()), "film_backward")
     return dz
 
 
@@ -260,28 +262,33 @@ def embed_gates(q_input, q_lens32, embed, w_ih, b_ih, b_hh):
     return gx
 
 
-def lstm_chain_forward(gx, q_lens32, whh_t, h_state, c_state, n_pass, save=False):
+def lstm_chain_forward(gx, q_lens32, whh_t, h_state, c_state, n_pass, save=False, want_states=False):
     B, L, H4 = gx.shape
     H = H4 // 4
     dev = gx.device
     h_pass = torch.empty(n_pass, B, H, device=dev, dtype=torch.float32)
+    states = torch.zeros(n_pass, B, L, H, device=dev, dtype=torch.float32) if want_states else None
     sg = sc = sh = None
     if save:
         sg = torch.zeros(n_pass, B, L, H4, device=dev, dtype=torch.float32)
         sc = torch.zeros(n_pass, B, L, H, device=dev, dtype=torch.float32)
         sh = torch.zeros(n_pass, B, L, H, device=dev, dtype=torch.float32)
     check(_lib.lib().vnqa_lstm_chain_forward(_p(gx), _p(q_lens32), _p(whh_t), _p(h_state), _p(c_state), n_pass, B, L, H,
-                                             _p(h_pass), _p(sg), _p(sc), _p(sh), _stream()), "lstm_chain_forward")
+                                             _p(h_pass), _p(sg), _p(sc), _p(sh), _p(states), _stream()),
+          "lstm_chain_forward")
+    if want_states:
+        return h_pass, sg, sc, sh, states
     return h_pass, sg, sc, sh
 
 
-def lstm_chain_backward(dh_pass, q_lens32, whh, save_gates, save_c, c0):
+def lstm_chain_backward(dh_pass, q_lens32, whh, save_gates, save_c, c0, dh_steps=None):
     n_pass, B, L, H4 = save_gates.shape
     H = H4 // 4
     dgates = torch.zeros_like(save_gates)
     dgx = torch.empty(B, L, H4, device=whh.device, dtype=torch.float32)
     check(_lib.lib().vnqa_lstm_chain_backward(_p(dh_pass), _p(q_lens32), _p(whh), _p(save_gates), _p(save_c), _p(c0),
-                                              n_pass, B, L, H, _p(dgates), _p(dgx), _stream()), "lstm_chain_backward")
+                                              n_pass, B, L, H, _p(dgates), _p(dgx), _p(dh_steps), _stream()),
+          "lstm_chain_backward")
     return dgates, dgx
 
 
@@ -298,6 +305,50 @@ def embed_backward(q_input, q_lens32, dx, dembed):
     check(_lib.lib().vnqa_embed_backward(_p(q_input), _p(q_lens32), _p(dx), B, L, dx.shape[-1], _p(dembed), _stream()),
           "embed_backward")
     return dembed
+
+
+# ------------------------------------------------------------------------------------------ multi-hop decoder
+def tmh_hops_forward(states, h_last, img_frame, img_clip, W, NB, enc_g, enc_b, w_att, b_att):
+    n_pass, B, L, H = states.shape
+    n_img = img_frame.numel()
+    dev = states.device
+    hvec = torch.empty(NB, n_img, H, device=dev, dtype=torch.float32)
+    enc_out = torch.empty(n_img, H, device=dev, dtype=torch.float32)
+    enc_stat = torch.empty(n_img, 2, device=dev, dtype=torch.float32)
+    coefs = torch.empty(NB, n_img, W, device=dev, dtype=torch.float32)
+    check(_lib.lib().vnqa_tmh_hops_forward(_p(states), _p(h_last), _p(img_frame), _p(img_clip), n_img, B, L, H, W, NB,
+                                           _p(enc_g), _p(enc_b), _p(w_att), _p(b_att), _p(hvec), _p(enc_out),
+                                           _p(enc_stat), _p(coefs), _stream()), "tmh_hops_forward")
+    return hvec, enc_out, enc_stat, coefs
+
+
+def tmh_hops_backward(states, h_last, img_frame, img_clip, q_lens32, W, NB, enc_g, w_att, hvec, enc_out, enc_stat,
+                      coefs, dhvec, dw_att, db_att, denc_g, denc_b):
+    n_pass, B, L, H = states.shape
+    n_img = img_frame.numel()
+    dstates = torch.zeros_like(states)
+    check(_lib.lib().vnqa_tmh_hops_backward(_p(states), _p(h_last), _p(img_frame), _p(img_clip), _p(q_lens32), n_img, B,
+                                            L, H, W, NB, _p(enc_g), _p(w_att), _p(hvec), _p(enc_out), _p(enc_stat),
+                                            _p(coefs), _p(dhvec), _p(dstates), _p(dw_att), _p(db_att), _p(denc_g),
+                                            _p(denc_b), _stream()), "tmh_hops_backward")
+    return dstates
+
+
+def ln_slice_forward(cond, gamma, beta, film_row, film, off, width):
+    rows, N = cond.shape
+    stat = torch.empty(rows, 2, device=cond.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_ln_slice_forward(_p(cond), rows, N, _p(gamma), _p(beta), _p(film_row), film.stride(0), off,
+                                           width, _p(film), _p(stat), _stream()), "ln_slice_forward")
+    return stat
+
+
+def ln_slice_backward(cond, gamma, film_row, dfilm, off, width, stat, dgamma, dbeta):
+    rows, N = cond.shape
+    dcond = torch.empty_like(cond)
+    check(_lib.lib().vnqa_ln_slice_backward(_p(cond), rows, N, _p(gamma), _p(film_row), dfilm.stride(0), off, width,
+                                            _p(dfilm), _p(stat), _p(dcond), _p(dgamma), _p(dbeta), _stream()),
+          "ln_slice_backward")
+    return dcond
 
 
 # ------------------------------------------------------------------------------------------ attention tail
