@@ -31,8 +31,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG = dict(c_in=512, C=1024, nb=5, hidden=128, at_hidden=128, embed=128, vocab=134, classes=70, T=35, Lq=56)
-FWD_GFLOP_PER_CLIP = 521.85
-TRAIN_GFLOP_PER_CLIP = 1522.61
+# eval.sh hyper-parameters per model (eval.sh:8-41) and algorithmic work per full-length clip
+MODELS = {
+    "attn": dict(nb=5, tail=None, fwd_gflop=521.85, train_gflop=1522.61, name="film_attn_pt"),
+    "gp": dict(nb=4, tail=32, fwd_gflop=425.51, train_gflop=1233.58, name="film_gp_pt"),
+    "tmh": dict(nb=3, tail=64, fwd_gflop=330.37, train_gflop=948.16, name="time_multi_hop"),
+}
 
 
 def parse():
@@ -42,6 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", choices=["train", "eval"], default="train")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--model", choices=list(MODELS), default="attn", help="attn = the headline metric")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU")
     ap.add_argument("--ragged", action="store_true", help="ragged v_lens (secondary config) instead of all 35")
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU sample")
@@ -50,15 +55,15 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------- CPU leg
-def cpu_leg(workload, clips, iters=1, warm=0):
+def cpu_leg(workload, clips, iters=1, warm=0, kind="attn"):
     """Time the CPU oracle (port of the reference forward/backward) on all host cores, bounded sample."""
     import torch
     from oracle import film_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    p = O.init_params("attn", c_in=CFG["c_in"], C=CFG["C"], nb=CFG["nb"], hidden=CFG["hidden"],
+    p = O.init_params(kind, c_in=CFG["c_in"], C=CFG["C"], nb=MODELS[kind]["nb"], hidden=CFG["hidden"],
                       at_hidden=CFG["at_hidden"], embed=CFG["embed"], vocab=CFG["vocab"], classes=CFG["classes"],
-                      T=CFG["T"], seed=1)
+                      tail=MODELS[kind]["tail"] or 32, T=CFG["T"], seed=1)
     v, q, v_lens, q_lens, labels = O.synthetic_batch(clips, c_in=CFG["c_in"], T=CFG["T"], Lq=CFG["Lq"],
                                                      vocab=CFG["vocab"], classes=CFG["classes"], seed=0)
     times = []
@@ -67,10 +72,10 @@ def cpu_leg(workload, clips, iters=1, warm=0):
         st = O.new_film_state(clips, CFG["hidden"])
         t0 = time.perf_counter()
         if workload == "train":
-            O.loss_and_grads("attn", p, bn, st, v, q, v_lens, q_lens, labels, training=True)
+            O.loss_and_grads(kind, p, bn, st, v, q, v_lens, q_lens, labels, training=True)
         else:
             with torch.no_grad():
-                O.film_attn_forward(p, bn, st, v, q, v_lens, q_lens, training=False)
+                O.FORWARDS[kind](p, bn, st, v, q, v_lens, q_lens, training=False)
         if i >= warm:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
@@ -128,9 +133,10 @@ class ClockSampler(threading.Thread):
 def gpu_leg(args):
     import torch
     import torch.distributed as dist
-    from oracle.film_oracle import synthetic_batch          # input generator only (numpy RNG); not timed
     from videonavqa_b200 import dp, ops
-    from videonavqa_b200.models import FiLMAttnPretrainedStem
+    from videonavqa_b200.synth import synthetic_batch
+    from videonavqa_b200.models import (FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem,
+                                        TimeMultiHopFiLMPretrainedStem)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -141,10 +147,17 @@ def gpu_leg(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(1)
-    model = FiLMAttnPretrainedStem(batch_size=B, q_embedding_size=CFG["embed"], nb_classes=CFG["classes"],
-                                   num_input_channels=CFG["c_in"], num_res_block_channels=CFG["C"],
-                                   num_res_blocks=CFG["nb"], hidden_size=CFG["hidden"], at_hidden_size=CFG["at_hidden"],
-                                   max_num_frames=CFG["T"], vocab_size=CFG["vocab"]).to(dev)
+    M = MODELS[args.model]
+    common = dict(batch_size=B, q_embedding_size=CFG["embed"], nb_classes=CFG["classes"],
+                  num_input_channels=CFG["c_in"], num_res_block_channels=CFG["C"], num_res_blocks=M["nb"],
+                  hidden_size=CFG["hidden"], vocab_size=CFG["vocab"])
+    if args.model == "attn":
+        model = FiLMAttnPretrainedStem(at_hidden_size=CFG["at_hidden"], max_num_frames=CFG["T"], **common)
+    elif args.model == "gp":
+        model = FiLMGlobalPoolingPretrainedStem(num_tail_channels=M["tail"], **common)
+    else:
+        model = TimeMultiHopFiLMPretrainedStem(num_tail_channels=M["tail"], **common)
+    model = model.to(dev)
     reducer = None
     if world > 1:
         dp.broadcast_module(model)
@@ -272,14 +285,15 @@ def gpu_leg(args):
                 "frac": round(k["tflops"] / tf32_peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "flops_per_launch": klass[dom_tag][2], "ms_per_launch": k["ms_per_launch"]}
     clips = B * world
-    gflop = TRAIN_GFLOP_PER_CLIP if train else FWD_GFLOP_PER_CLIP
+    gflop = M["train_gflop"] if train else M["fwd_gflop"]
+    mname = {"attn": "FiLM-attn", "gp": "FiLM-gp", "tmh": "time-multi-hop"}[args.model]
     scale = n_frames_total / (B * CFG["T"])
     out = {
-        "metric": "video-QA clips/sec (FiLM-attn fwd+bwd)" if train else "video-QA clips/sec (FiLM-attn eval forward)",
+        "metric": f"video-QA clips/sec ({mname} fwd+bwd)" if train else f"video-QA clips/sec ({mname} eval forward)",
         "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32 operands, fp32 accumulate/storage", "data": "synthetic",
-        "config": {"workload": f"film_attn_pt {args.workload} step, eval.sh hyper-parameters (C_in 512, C 1024, 5 blocks,"
+        "config": {"workload": f"{M['name']} {args.workload} step, eval.sh hyper-parameters (C_in 512, C 1024, {M['nb']} blocks,"
                                f" hidden 128, 70 classes), {B} clips/GPU x 35 frames x 512x10x13"
                                + (", ragged v_lens" if args.ragged else ", all clips 35 frames"),
                    "global_batch": clips, "frames_per_clip": CFG["T"], "parallelism": f"dp{world}",
@@ -308,7 +322,7 @@ def main():
         if rank != 0:
             return
         iters = max(1, min(args.steps, 3))
-        cb = cpu_leg(args.workload, args.cpu_clips, iters=iters, warm=min(args.warmup, 1))
+        cb = cpu_leg(args.workload, args.cpu_clips, iters=iters, warm=min(args.warmup, 1), kind=args.model)
         line = {"impl": "reference",
                 "metric": "video-QA clips/sec (FiLM-attn fwd+bwd)" if args.workload == "train"
                 else "video-QA clips/sec (FiLM-attn eval forward)",
@@ -326,7 +340,7 @@ def main():
     if out is None:
         return
     if args.gpus == 1 and not args.no_cpu:
-        cb = cpu_leg(args.workload, args.cpu_clips)
+        cb = cpu_leg(args.workload, args.cpu_clips, kind=args.model)
         out["cpu_baseline"] = {k: (round(cb[k], 4) if k == "value" else cb[k])
                                for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(out))

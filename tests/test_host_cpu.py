@@ -120,3 +120,19 @@ def test_plan_matches_reference_frame_loop():
     assert int(p.feat_row[img_of[1, 3]]) == 1 * 35 + 3
     with pytest.raises(ValueError):
         Plan([3, 5], 2, 35, torch.device("cpu"))
+
+
+def test_product_and_oracle_input_generators_agree():
+    from oracle.film_oracle import synthetic_batch as a
+    from videonavqa_b200.synth import synthetic_batch as b
+    for kw in (dict(B=3, c_in=32, seed=4), dict(B=5, c_in=32, seed=9, ragged=True)):
+        for x, y in zip(a(**kw), b(**kw)):
+            assert torch.equal(x, y)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under videonavqa_b200/ may import it."""
+    import glob
+    for f in glob.glob(os.path.join(ROOT, "videonavqa_b200", "**", "*.py"), recursive=True):
+        src = open(f).read()
+        assert "import oracle" not in src and "from oracle" not in src, f
