@@ -5,39 +5,52 @@
 //
 //   D[co][pix] = sum_{tap, ci} Wp[tap][co][ci] * X[pix (+) tap][ci]
 //
-// Orientation: the UMMA M dimension (128 TMEM lanes) is the OUTPUT CHANNEL, the N dimension (208 TMEM
-// columns) is a block of pixels = 8 frame images x 2 image rows x 13 columns.  130-pixel images do not
-// tile by 128, but 13*16 = 208 is a legal UMMA N, so no MMA work is wasted on padding.  The pixel block of
-// filter tap (dy,dx) is one 4-D TMA box {32 ch, 13 w, 2 h, 8 img} at coordinate {k, dx, h0+dy, n0}; the
-// zero halo of the 3x3 filter is the TMA out-of-bounds fill, so activations are stored unpadded.
+// Orientation: the UMMA M dimension (TMEM lanes) is the OUTPUT CHANNEL, the N dimension (208 TMEM columns) is a
+// block of pixels = 8 frame images x 2 image rows x 13 columns.  130-pixel images do not tile by 128, but
+// 13*16 = 208 is a legal UMMA N, so no MMA work is wasted on padding.  The pixel block of filter tap (dy,dx) is a
+// 4-D TMA box {32 ch, 13 w, 2 h, images} at coordinate {k, dx, h0+dy, n0}; the zero halo of the 3x3 filter is the
+// TMA out-of-bounds fill, so activations are stored unpadded.
 //
-// Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warps 4-7 =
-// epilogue (TMEM -> registers -> fused math -> coalesced global stores; one thread per output channel).
-// 5 smem stages of {A 128x32, B 208x32} fp32 with 128-byte swizzle; accumulators double-buffered in TMEM
-// (2 x 208 columns) so the epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs, static
-// round-robin tile schedule.
+// Two variants of the same pipeline (template NCTA):
+//   NCTA = 2 (whenever Cout spans an even number of 128-row tiles): a CTA PAIR on one TPC executes
+//     tcgen05.mma.cta_group::2 with M = 256 - each CTA stages its own 128 weight rows and HALF of the pixel block
+//     (4 of the 8 images), so per-SM L2->smem traffic drops from 42 KB to 29 KB per K-step and 7 stages fit; only
+//     the leader issues MMAs, commits are multicast to both CTAs' barriers, each CTA drains its own TMEM half.
+//   NCTA = 1: single-CTA 128 x 208 tiles, 5 stages (odd tile counts: 128-row GEMMs, tail convolutions).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-7 epilogue
+// (TMEM -> registers -> fused math -> coalesced global stores; one thread per output channel).  Accumulators are
+// double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
 namespace vnqa {
 
-constexpr int BM = 128;            // output channels per tile (TMEM lanes)
+constexpr int BM = 128;            // output channels per CTA tile (TMEM lanes)
 constexpr int BN = 208;            // pixels per tile (TMEM columns) = 8 * 2 * 13
 constexpr int BK = 32;             // fp32 reduction elements per stage = one 128-byte swizzle row
 constexpr int UMMA_K = 8;          // tf32: 32 bytes per instruction
-constexpr int STAGES = 5;
 constexpr int A_BYTES = BM * BK * 4;           // 16384
-constexpr int B_BYTES = BN * BK * 4;           // 26624 (multiple of 1024)
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 43008
 constexpr int ACC_COLS = 256;                  // TMEM column stride between the two accumulator stages
 constexpr int TMEM_COLS = 512;
 constexpr int IMG_PER_TILE = 8;
 constexpr int ROWS_PER_IMG_TILE = 26;          // 2 image rows x 13
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 256;
+
+template <int NCTA>
+struct Cfg {
+  static constexpr int B_ROWS = BN / NCTA;                 // pixel rows staged per CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 4;          // 26624 / 13312 (multiples of 1024)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 43008 / 29696
+  static constexpr int STAGES = NCTA == 1 ? 5 : 7;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct KParams {
   int taps, k_chunks, m_tiles, n_tiles, splits, rows_pad, flat, cout, n_img, epi, no_round;
+  int debug_n;  // debug 2 only: override the MMA N (timing experiments)
+  int debug;  // bring-up experiments (VNQA_CONV_DEBUG): 1 skip B loads, 2 skip all loads, 3 skip MMAs; results are garbage
   long long out_split_stride;  // PARTIAL: n_img * cout
   float* out;
   const float* bias;
@@ -60,65 +73,197 @@ __device__ __forceinline__ float rnd(float x, int no_round) { return no_round ? 
 struct TileCoord {
   int mt, nt, sp;
 };
-__device__ __forceinline__ TileCoord decode_tile(int tile, const KParams& p) {
+// work item -> tile of THIS CTA.  Items enumerate (m-tile group, n-tile, split) with the m index fastest so that
+// co-resident CTAs share activation tiles in L2; a CTA pair shares one item and takes m-tiles 2g and 2g+1.
+template <int NCTA>
+__device__ __forceinline__ TileCoord decode_tile(int item, const KParams& p, int rank) {
+  const int mg = p.m_tiles / NCTA;
   TileCoord t;
-  t.mt = tile % p.m_tiles;
-  int r = tile / p.m_tiles;
+  t.mt = (item % mg) * NCTA + rank;
+  const int r = item / mg;
   t.nt = r % p.n_tiles;
   t.sp = r / p.n_tiles;
   return t;
 }
 
+// ------------------------------------------------------------------------------------------------ epilogue
+// One accumulator tile (128 channels x 208 pixels) from TMEM to global memory; thread = output channel.
 template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord& tc, uint32_t t_base, int ew,
+                                              int lane) {
+  const int co = tc.mt * BM + ew * 32 + lane;
+  const bool co_ok = co < p.cout;
+  float bias = 0.f, scale = 1.f, shift = 0.f;
+  if (EPI == VNQA_EPI_BIAS_RELU || EPI == VNQA_EPI_BIAS_RELU_AFFINE || EPI == VNQA_EPI_BIAS_RELU_STATS ||
+      EPI == VNQA_EPI_FILM) {
+    if (co_ok) bias = __ldg(p.bias + co);
+  }
+  if (EPI == VNQA_EPI_BIAS_RELU_AFFINE && co_ok) {
+    scale = __ldg(p.scale + co);
+    shift = __ldg(p.shift + co);
+  }
+  float* out = p.out;
+  if (EPI == VNQA_EPI_PARTIAL) out += (long long)tc.sp * p.out_split_stride;
+
+  double st_sum = 0.0, st_sq = 0.0;  // STATS: running per-frame accumulators
+  int st_frame = -1;
+  float db_acc = 0.f;                // DGRAD_RES: per-channel sum
+
+#pragma unroll 1
+  for (int nl = 0; nl < IMG_PER_TILE; ++nl) {
+    uint32_t v[ROWS_PER_IMG_TILE];
+    tmem_ld_x16(t_base + nl * ROWS_PER_IMG_TILE, v);
+    tmem_ld_x8(t_base + nl * ROWS_PER_IMG_TILE + 16, v + 16);
+    tmem_ld_x2(t_base + nl * ROWS_PER_IMG_TILE + 24, v + 24);
+    tmem_ld_wait();
+
+    long long row0;  // first output row of this 26-column group
+    int nvalid;      // valid rows in the group
+    int img = 0;
+    if (p.flat) {
+      row0 = (long long)tc.nt * BN + nl * ROWS_PER_IMG_TILE;
+      long long rem = (long long)p.n_img - row0;
+      nvalid = rem >= ROWS_PER_IMG_TILE ? ROWS_PER_IMG_TILE : (rem > 0 ? (int)rem : 0);
+    } else {
+      img = (tc.nt / 5) * IMG_PER_TILE + nl;
+      row0 = (long long)img * VNQA_IMG_PIX + (tc.nt % 5) * ROWS_PER_IMG_TILE;
+      nvalid = img < p.n_img ? ROWS_PER_IMG_TILE : 0;
+    }
+    if (nvalid > 0 && co_ok) {
+    float* orow = out + row0 * p.cout + co;
+
+    if (EPI == VNQA_EPI_BIAS_RELU) {
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+        if (r < nvalid) orow[(long long)r * p.cout] = rnd(fmaxf(__uint_as_float(v[r]) + bias, 0.f), p.no_round);
+    } else if (EPI == VNQA_EPI_BIAS_RELU_AFFINE) {
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+        if (r < nvalid) orow[(long long)r * p.cout] = rnd(fmaf(fmaxf(__uint_as_float(v[r]) + bias, 0.f), scale, shift), p.no_round);
+    } else if (EPI == VNQA_EPI_BIAS_RELU_STATS) {
+      const int fr = __ldg(p.img_frame + img);
+      if (fr != st_frame) {
+        if (st_frame >= 0) {
+          atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
+          atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
+        }
+        st_frame = fr; st_sum = 0.0; st_sq = 0.0;
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+        const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
+        orow[(long long)r * p.cout] = y;
+        s1 += y;
+        s2 = fmaf(y, y, s2);
+      }
+      st_sum += (double)s1;
+      st_sq += (double)s2;
+    } else if (EPI == VNQA_EPI_FILM) {
+      const float* frow = p.film + (long long)__ldg(p.film_row + img) * p.film_ld + p.alpha_off;
+      const float alpha = __ldg(frow + co);
+      const float beta = __ldg(frow + p.cout + co);
+      const float* rrow = p.res + row0 * p.cout + co;
+      float rv[ROWS_PER_IMG_TILE];
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) rv[r] = __ldg(rrow + (long long)r * p.cout);
+      if (p.z_out != nullptr) {
+        float* zrow = p.z_out + row0 * p.cout + co;
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) zrow[(long long)r * p.cout] = __uint_as_float(v[r]) + bias;
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+        const float z = __uint_as_float(v[r]) + bias;
+        orow[(long long)r * p.cout] = rnd(fmaxf(fmaf(alpha, z, beta), 0.f) + rv[r], p.no_round);
+      }
+    } else if (EPI == VNQA_EPI_PARTIAL || EPI == VNQA_EPI_PLAIN) {
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+        if (r < nvalid) orow[(long long)r * p.cout] = __uint_as_float(v[r]);
+    } else if (EPI == VNQA_EPI_DGRAD_RES) {
+      const float* arow = p.add + row0 * p.cout + co;
+      const float* mrow = p.res + row0 * p.cout + co;
+      float av[ROWS_PER_IMG_TILE], mv[ROWS_PER_IMG_TILE];
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+        av[r] = __ldg(arow + (long long)r * p.cout);
+        mv[r] = __ldg(mrow + (long long)r * p.cout);
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+        const float g = mv[r] > 0.f ? tf32_round(__uint_as_float(v[r]) + av[r]) : 0.f;
+        orow[(long long)r * p.cout] = g;
+        db_acc += g;
+      }
+    }
+    }  // nvalid && co_ok
+    __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+  }
+  if (EPI == VNQA_EPI_BIAS_RELU_STATS && st_frame >= 0 && co_ok) {
+    atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
+    atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
+  }
+  if (EPI == VNQA_EPI_DGRAD_RES && p.dbias != nullptr && co_ok) atomicAdd(p.dbias + co, db_acc);
+
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int EPI, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+  using C = Cfg<NCTA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* acc_full = empty_bar + C::STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int total_items = (p.m_tiles / NCTA) * p.n_tiles * p.splits;
+  const int first_item = blockIdx.x / NCTA;
+  const int item_stride = gridDim.x / NCTA;
   const int k_iters = p.taps * p.k_chunks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], NCTA);        // one producer arrival per CTA (+ the TMA byte count)
+      mbar_init(&empty_bar[i], 1);          // one (multicast) MMA commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[i], 4 * NCTA);   // one arrive per epilogue warp of every CTA
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (NCTA == 2) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (every CTA)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(tile, p);
+    for (int item = first_item; item < total_items; item += item_stride) {
+      const TileCoord tc = decode_tile<NCTA>(item, p, rank);
       const int a_row0 = tc.mt * BM;
       int b1, b2, b3;  // B box coordinates of dims 1..3 before the tap shift
       if (p.flat) {
-        b1 = tc.nt * BN; b2 = 0; b3 = 0;
+        b1 = tc.nt * BN + rank * C::B_ROWS; b2 = 0; b3 = 0;
       } else {
-        b1 = 0; b2 = (tc.nt % 5) * 2; b3 = (tc.nt / 5) * IMG_PER_TILE;
+        b1 = 0; b2 = (tc.nt % 5) * 2; b3 = (tc.nt / 5) * IMG_PER_TILE + rank * (IMG_PER_TILE / NCTA);
       }
       const int k_base = tc.sp * p.k_chunks * BK;
       for (int tap = 0; tap < p.taps; ++tap) {
@@ -126,199 +271,131 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          if (lane == 0) {
-            uint8_t* sa = smem + stage * STAGE_BYTES;
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
-            tma_load_4d(&tmB, &full_bar[stage], sb, k_base + kc * BK, b1 + dx, b2 + dy, b3);
+            if (NCTA == 1 && p.debug == 1) {
+              mbar_expect_tx(&full_bar[stage], A_BYTES);
+              tma_load_2d(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
+            } else if (NCTA == 1 && p.debug == 2) {
+              mbar_arrive(&full_bar[stage]);
+            } else if (NCTA == 1) {
+              mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              tma_load_2d(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
+              tma_load_4d(&tmB, &full_bar[stage], sb, k_base + kc * BK, b1 + dx, b2 + dy, b3);
+            } else {
+              // both CTAs' bytes land on the leader's barrier; the peer adds its arrival remotely
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+              tma_load_2d_2sm(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
+              tma_load_4d_2sm(&tmB, &full_bar[stage], sb, k_base + kc * BK, b1 + dx, b2 + dy, b3);
+              if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
+            }
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    const uint32_t idesc = (p.debug == 2 && p.debug_n > 0) ? umma_idesc_tf32(BM * NCTA, p.debug_n, 0, 0)
+                                                          : umma_idesc_tf32(BM * NCTA, BN, 0, 0);
     constexpr uint64_t dbase = umma_desc_base_sw128(16, 1024);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = first_item; item < total_items; item += item_stride) {
       mbar_wait(&acc_empty[as], aphase ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * ACC_COLS;
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = umma_desc(dbase, sa);
           const uint64_t bdesc = umma_desc(dbase, sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (>>4 = 2) inside the 128-byte swizzle row
-            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if (p.debug == 3) continue;
+            if (NCTA == 1) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else umma_tf32_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
-          if (it == k_iters - 1) umma_commit(&acc_full[as]);    // accumulator complete -> epilogue
+          if (NCTA == 1) {
+            umma_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
+            if (it == k_iters - 1) umma_commit(&acc_full[as]);    // accumulator complete -> epilogue
+          } else {
+            umma_commit_2sm(&empty_bar[stage], 0x3);              // ... in both CTAs of the pair
+            if (it == k_iters - 1) umma_commit_2sm(&acc_full[as], 0x3);
+          }
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (every CTA, own TMEM half)
     const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(tile, p);
-      const int co = tc.mt * BM + ew * 32 + lane;
-      const bool co_ok = co < p.cout;
-      float bias = 0.f, scale = 1.f, shift = 0.f;
-      if (EPI == VNQA_EPI_BIAS_RELU || EPI == VNQA_EPI_BIAS_RELU_AFFINE || EPI == VNQA_EPI_BIAS_RELU_STATS ||
-          EPI == VNQA_EPI_FILM) {
-        if (co_ok) bias = __ldg(p.bias + co);
-      }
-      if (EPI == VNQA_EPI_BIAS_RELU_AFFINE && co_ok) {
-        scale = __ldg(p.scale + co);
-        shift = __ldg(p.shift + co);
-      }
-      float* out = p.out;
-      if (EPI == VNQA_EPI_PARTIAL) out += (long long)tc.sp * p.out_split_stride;
-
-      double st_sum = 0.0, st_sq = 0.0;  // STATS: running per-frame accumulators
-      int st_frame = -1;
-      float db_acc = 0.f;                // DGRAD_RES: per-channel sum
-
+    for (int item = first_item; item < total_items; item += item_stride) {
+      const TileCoord tc = decode_tile<NCTA>(item, p, rank);
       mbar_wait(&acc_full[as], aphase, 4);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * ACC_COLS;
-
-#pragma unroll 1
-      for (int nl = 0; nl < IMG_PER_TILE; ++nl) {
-        uint32_t v[ROWS_PER_IMG_TILE];
-        tmem_ld_x16(t_base + nl * ROWS_PER_IMG_TILE, v);
-        tmem_ld_x8(t_base + nl * ROWS_PER_IMG_TILE + 16, v + 16);
-        tmem_ld_x2(t_base + nl * ROWS_PER_IMG_TILE + 24, v + 24);
-        tmem_ld_wait();
-
-        long long row0;  // first output row of this 26-column group
-        int nvalid;      // valid rows in the group
-        int img = 0;
-        if (p.flat) {
-          row0 = (long long)tc.nt * BN + nl * ROWS_PER_IMG_TILE;
-          long long rem = (long long)p.n_img - row0;
-          nvalid = rem >= ROWS_PER_IMG_TILE ? ROWS_PER_IMG_TILE : (rem > 0 ? (int)rem : 0);
-        } else {
-          img = (tc.nt / 5) * IMG_PER_TILE + nl;
-          row0 = (long long)img * VNQA_IMG_PIX + (tc.nt % 5) * ROWS_PER_IMG_TILE;
-          nvalid = img < p.n_img ? ROWS_PER_IMG_TILE : 0;
-        }
-        if (nvalid > 0 && co_ok) {
-        float* orow = out + row0 * p.cout + co;
-
-        if (EPI == VNQA_EPI_BIAS_RELU) {
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
-            if (r < nvalid) orow[(long long)r * p.cout] = rnd(fmaxf(__uint_as_float(v[r]) + bias, 0.f), p.no_round);
-        } else if (EPI == VNQA_EPI_BIAS_RELU_AFFINE) {
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
-            if (r < nvalid) orow[(long long)r * p.cout] = rnd(fmaf(fmaxf(__uint_as_float(v[r]) + bias, 0.f), scale, shift), p.no_round);
-        } else if (EPI == VNQA_EPI_BIAS_RELU_STATS) {
-          const int fr = __ldg(p.img_frame + img);
-          if (fr != st_frame) {
-            if (st_frame >= 0) {
-              atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
-              atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
-            }
-            st_frame = fr; st_sum = 0.0; st_sq = 0.0;
-          }
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-            const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
-            orow[(long long)r * p.cout] = y;
-            s1 += y;
-            s2 = fmaf(y, y, s2);
-          }
-          st_sum += (double)s1;
-          st_sq += (double)s2;
-        } else if (EPI == VNQA_EPI_FILM) {
-          const float* frow = p.film + (long long)__ldg(p.film_row + img) * p.film_ld + p.alpha_off;
-          const float alpha = __ldg(frow + co);
-          const float beta = __ldg(frow + p.cout + co);
-          const float* rrow = p.res + row0 * p.cout + co;
-          float rv[ROWS_PER_IMG_TILE];
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) rv[r] = __ldg(rrow + (long long)r * p.cout);
-          if (p.z_out != nullptr) {
-            float* zrow = p.z_out + row0 * p.cout + co;
-#pragma unroll
-            for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) zrow[(long long)r * p.cout] = __uint_as_float(v[r]) + bias;
-          }
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-            const float z = __uint_as_float(v[r]) + bias;
-            orow[(long long)r * p.cout] = rnd(fmaxf(fmaf(alpha, z, beta), 0.f) + rv[r], p.no_round);
-          }
-        } else if (EPI == VNQA_EPI_PARTIAL || EPI == VNQA_EPI_PLAIN) {
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
-            if (r < nvalid) orow[(long long)r * p.cout] = __uint_as_float(v[r]);
-        } else if (EPI == VNQA_EPI_DGRAD_RES) {
-          const float* arow = p.add + row0 * p.cout + co;
-          const float* mrow = p.res + row0 * p.cout + co;
-          float av[ROWS_PER_IMG_TILE], mv[ROWS_PER_IMG_TILE];
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-            av[r] = __ldg(arow + (long long)r * p.cout);
-            mv[r] = __ldg(mrow + (long long)r * p.cout);
-          }
-#pragma unroll
-          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-            const float g = mv[r] > 0.f ? tf32_round(__uint_as_float(v[r]) + av[r]) : 0.f;
-            orow[(long long)r * p.cout] = g;
-            db_acc += g;
-          }
-        }
-        }  // nvalid && co_ok
-        __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
-      }
-      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      epilogue_tile<EPI>(p, tc, t_base, ew, lane);
+      // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
-
-      if (EPI == VNQA_EPI_BIAS_RELU_STATS && st_frame >= 0 && co_ok) {
-        atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
-        atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
+      if (lane == 0) {
+        if (leader) mbar_arrive(&acc_empty[as]);
+        else mbar_arrive_remote(&acc_empty[as], 0);
       }
-      if (EPI == VNQA_EPI_DGRAD_RES && p.dbias != nullptr && co_ok) atomicAdd(p.dbias + co, db_acc);
-
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's smem until the end
+  if (warp == 2) {
+    if (NCTA == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI, int NCTA>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int sms, cudaStream_t st) {
+  auto kern = conv_gemm_kernel<EPI, NCTA>;
+  constexpr int smem = Cfg<NCTA>::SMEM_BYTES;
+  VNQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int items = (kp.m_tiles / NCTA) * kp.n_tiles * kp.splits;
+  const int groups = sms / NCTA;
+  const int grid = (items < groups ? items : groups) * NCTA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = NCTA == 2 ? 1 : 0;
+  VNQA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, kp));
+  return 0;
 }
 
 template <int EPI>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int grid, cudaStream_t st) {
-  auto kern = conv_gemm_kernel<EPI>;
-  VNQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, kp);
-  VNQA_CHECK_CUDA(cudaGetLastError());
-  return 0;
+static int launch_any(int ncta, const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int sms,
+                      cudaStream_t st) {
+  return ncta == 2 ? launch<EPI, 2>(tmA, tmB, kp, sms, st) : launch<EPI, 1>(tmA, tmB, kp, sms, st);
 }
 
 }  // namespace vnqa
@@ -347,11 +424,17 @@ extern "C" int vnqa_conv_gemm(const vnqa_conv_args* a, void* stream) {
   kp.n_img = a->n_img;
   kp.epi = a->epi;
   kp.no_round = a->no_round;
+  { const char* e = getenv("VNQA_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("VNQA_CONV_DEBUG_N"); kp.debug_n = e ? atoi(e) : 0; }
   kp.out_split_stride = (long long)a->n_img * a->cout;
   kp.out = a->out; kp.bias = a->bias; kp.scale = a->scale; kp.shift = a->shift;
   kp.img_frame = a->img_frame; kp.stat_sum = a->stat_sum; kp.stat_sq = a->stat_sq;
   kp.film = a->film; kp.film_row = a->film_row; kp.film_ld = a->film_ld; kp.alpha_off = a->alpha_off;
   kp.res = a->res; kp.z_out = a->z_out; kp.add = a->add; kp.dbias = a->dbias;
+
+  // CTA pairs (cta_group::2) whenever the output channels split into an even number of 128-row tiles
+  int ncta = (kp.m_tiles % 2 == 0) ? 2 : 1;
+  if (const char* e = getenv("VNQA_CONV_NCTA")) ncta = (atoi(e) == 1 || kp.m_tiles % 2) ? 1 : 2;   // bring-up switch
 
   // A: packed weights, 2-D {K, rows}
   CUtensorMap tmA, tmB;
@@ -367,42 +450,40 @@ extern "C" int vnqa_conv_gemm(const vnqa_conv_args* a, void* stream) {
     VNQA_REQUIRE(ld >= (uint64_t)a->cin * splits && ld % 4 == 0, "vnqa_conv_gemm: bad x_ld");
     const uint64_t dims[4] = {(uint64_t)a->cin * splits, (uint64_t)a->n_img, 1, 1};
     const uint64_t strides[3] = {ld * 4, ld * 4 * (uint64_t)a->n_img, ld * 4 * (uint64_t)a->n_img};
-    const uint32_t box[4] = {BK, BN, 1, 1};
+    const uint32_t box[4] = {BK, (uint32_t)(BN / ncta), 1, 1};
     if (make_tmap_f32(&tmB, a->x, 4, dims, strides, box)) return -3;
   } else {
     const uint64_t c = (uint64_t)a->cin;
     const uint64_t dims[4] = {c, VNQA_IMG_W, VNQA_IMG_H, (uint64_t)a->n_img};
     const uint64_t strides[3] = {c * 4, c * 4 * VNQA_IMG_W, c * 4 * VNQA_IMG_PIX};
-    const uint32_t box[4] = {BK, VNQA_IMG_W, 2, IMG_PER_TILE};
+    const uint32_t box[4] = {BK, VNQA_IMG_W, 2, (uint32_t)(IMG_PER_TILE / ncta)};
     if (make_tmap_f32(&tmB, a->x, 4, dims, strides, box)) return -3;
   }
 
-  const int total = kp.m_tiles * kp.n_tiles * kp.splits;
   int sms = vnqa_sm_count();
   if (sms <= 0) return -2;
-  const int grid = total < sms ? total : sms;
   cudaStream_t st = as_stream(stream);
   switch (a->epi) {
     case VNQA_EPI_BIAS_RELU:
       VNQA_REQUIRE(a->bias, "conv_gemm: BIAS_RELU needs bias");
-      return launch<VNQA_EPI_BIAS_RELU>(tmA, tmB, kp, grid, st);
+      return launch_any<VNQA_EPI_BIAS_RELU>(ncta, tmA, tmB, kp, sms, st);
     case VNQA_EPI_BIAS_RELU_AFFINE:
       VNQA_REQUIRE(a->bias && a->scale && a->shift, "conv_gemm: AFFINE needs bias/scale/shift");
-      return launch<VNQA_EPI_BIAS_RELU_AFFINE>(tmA, tmB, kp, grid, st);
+      return launch_any<VNQA_EPI_BIAS_RELU_AFFINE>(ncta, tmA, tmB, kp, sms, st);
     case VNQA_EPI_BIAS_RELU_STATS:
       VNQA_REQUIRE(!a->flat && a->bias && a->img_frame && a->stat_sum && a->stat_sq, "conv_gemm: STATS operands");
-      return launch<VNQA_EPI_BIAS_RELU_STATS>(tmA, tmB, kp, grid, st);
+      return launch_any<VNQA_EPI_BIAS_RELU_STATS>(ncta, tmA, tmB, kp, sms, st);
     case VNQA_EPI_FILM:
       VNQA_REQUIRE(!a->flat && a->bias && a->film && a->film_row && a->res, "conv_gemm: FILM operands");
-      return launch<VNQA_EPI_FILM>(tmA, tmB, kp, grid, st);
+      return launch_any<VNQA_EPI_FILM>(ncta, tmA, tmB, kp, sms, st);
     case VNQA_EPI_PARTIAL:
-      return launch<VNQA_EPI_PARTIAL>(tmA, tmB, kp, grid, st);
+      return launch_any<VNQA_EPI_PARTIAL>(ncta, tmA, tmB, kp, sms, st);
     case VNQA_EPI_PLAIN:
       VNQA_REQUIRE(splits == 1, "conv_gemm: PLAIN cannot split K");
-      return launch<VNQA_EPI_PLAIN>(tmA, tmB, kp, grid, st);
+      return launch_any<VNQA_EPI_PLAIN>(ncta, tmA, tmB, kp, sms, st);
     case VNQA_EPI_DGRAD_RES:
       VNQA_REQUIRE(!a->flat && a->add && a->res, "conv_gemm: DGRAD_RES operands");
-      return launch<VNQA_EPI_DGRAD_RES>(tmA, tmB, kp, grid, st);
+      return launch_any<VNQA_EPI_DGRAD_RES>(ncta, tmA, tmB, kp, sms, st);
     default:
       set_error("vnqa_conv_gemm: unknown epilogue %d", a->epi);
       return -1;

@@ -88,7 +88,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int c_end = min(c_begin + p.chunks_per_split, p.n_chunks);
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-        if (lane == 0) {
+        if (elect_one()) {
           uint8_t* sa = smem + stage * WG_STAGE_BYTES;
           uint8_t* sb = sa + WG_A_BYTES;
           mbar_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
@@ -125,7 +125,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
         if (p.debug == 3 && blockIdx.x == 0 && lane == 0) printf("wgrad dbg: mma got chunk %d stage %d\n", c, stage);
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
           const uint64_t adesc = umma_desc(dbase, sa);
           const uint64_t bdesc = umma_desc(dbase, sa + WG_A_BYTES);
