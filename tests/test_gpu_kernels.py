@@ -1,0 +1,92 @@
+"""Kernel-level GPU checks through the C ABI (ctypes): the standalone CUDA harnesses (naive fp64 CUDA references for
+the tcgen05 conv / wgrad kernels) and a few direct comparisons against the oracle's arithmetic."""
+import os
+import subprocess
+
+import pytest
+import torch
+
+from oracle import film_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("binary", ["test_conv_gemm", "test_wgrad"])
+def test_standalone_cuda_harness(binary):
+    exe = os.path.join(ROOT, "build", binary)
+    assert os.path.exists(exe), "build/ is produced by __graft_entry__.build()"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_frames_to_nhwc_is_exact_tf32_rounding():
+    """K0 is pure data movement + one round-to-nearest to tf32: bit-exact against the oracle's rounding."""
+    from videonavqa_b200 import ops
+    from videonavqa_b200.engine import Plan
+    B, C, T = 5, 64, 35
+    v, _, _, _, _ = O.synthetic_batch(B, c_in=C, seed=3)
+    v_lens = [35, 20, 20, 7, 1]
+    plan = Plan(v_lens, B, T, torch.device("cuda"))
+    x = ops.frames_to_nhwc(v.cuda(), plan.img_of, plan.n_img).cpu()
+    img_of = plan.img_of.view(B, T).cpu()
+    for b, t in ((0, 0), (0, 34), (1, 19), (3, 6), (4, 0)):
+        ref = O.tf32_round(v[b, :, :, :, t].permute(1, 2, 0).reshape(130, C).contiguous())
+        assert torch.equal(x[int(img_of[b, t])], ref)
+    assert int((img_of >= 0).sum()) == plan.n_img == sum(v_lens)
+
+
+def test_sgemm_variants_match_fp64():
+    from videonavqa_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(300, 70, generator=g).cuda()
+    w = torch.randn(45, 70, generator=g).cuda()
+    b = torch.randn(45, generator=g).cuda()
+    dy = torch.randn(300, 45, generator=g).cuda()
+    ref = (x.double() @ w.double().t() + b.double()).clamp_min(0)
+    assert (ops.linear(x, w, b, relu=True).double() - ref).abs().max() < 1e-4
+    assert (ops.linear_dgrad(dy, w).double() - dy.double() @ w.double()).abs().max() < 1e-4
+    ref_w = dy.double().t() @ x.double()
+    assert (ops.linear_wgrad(dy, x).double() - ref_w).abs().max() < 1e-3
+    assert (ops.linear_wgrad(dy, x, ksplit=7).double() - ref_w).abs().max() < 1e-3
+    assert (ops.colsum(dy).double() - dy.double().sum(0)).abs().max() < 1e-4
+
+
+def test_question_lstm_chain_matches_oracle():
+    """35 chained packed-LSTM passes (Q3) against the oracle's step-by-step LSTM, forward state and BPTT gradients."""
+    from videonavqa_b200 import ops
+    B, L, E, H, n_pass = 6, 14, 48, 64, 5
+    g = torch.Generator().manual_seed(1)
+    emb = torch.randn(30, E, generator=g)
+    w_ih = torch.randn(4 * H, E, generator=g) * 0.2
+    w_hh = torch.randn(4 * H, H, generator=g) * 0.2
+    b_ih, b_hh = torch.randn(4 * H, generator=g) * 0.1, torch.randn(4 * H, generator=g) * 0.1
+    q_lens = torch.tensor([14, 3, 9, 1, 14, 6])
+    q = torch.randint(1, 30, (B, L), generator=g)
+    # oracle
+    p = [t.clone().requires_grad_(True) for t in (emb, w_ih, w_hh, b_ih, b_hh)]
+    h, c = torch.zeros(B, H), torch.zeros(B, H)
+    outs = []
+    for _ in range(n_pass):
+        _, h, c = O.packed_lstm_pass(torch.nn.functional.embedding(q, p[0]), q_lens, h, c, p[1], p[2], p[3], p[4])
+        outs.append(h)
+    h_ref = torch.stack(outs)
+    wgt = torch.randn(n_pass, B, H, generator=g)
+    (h_ref * wgt).sum().backward()
+    # CUDA
+    dev = torch.device("cuda")
+    ql32 = q_lens.to(dev, torch.int32)
+    gx = ops.embed_gates(q.to(dev), ql32, emb.to(dev), w_ih.to(dev), b_ih.to(dev), b_hh.to(dev))
+    hs, cs = torch.zeros(B, H, device=dev), torch.zeros(B, H, device=dev)
+    c0 = cs.clone()
+    h_pass, sg, sc, sh = ops.lstm_chain_forward(gx, ql32, w_hh.t().contiguous().to(dev), hs, cs, n_pass, save=True)
+    assert (h_pass.cpu() - h_ref.detach()).abs().max() < 1e-5
+    assert (hs.cpu() - h.detach()).abs().max() < 1e-5 and (cs.cpu() - c.detach()).abs().max() < 1e-5
+    dgates, dgx = ops.lstm_chain_backward(wgt.to(dev), ql32, w_hh.to(dev), sg, sc, c0)
+    steps = n_pass * B * L
+    dw_hh = ops.linear_wgrad(dgates.view(steps, 4 * H), sh.view(steps, H), ksplit=4).cpu()
+    assert (dw_hh - p[2].grad).abs().max() < 1e-4 * p[2].grad.abs().max().clamp_min(1)
+    xemb = ops.embed_gather(q.to(dev), ql32, emb.to(dev))
+    dw_ih = ops.linear_wgrad(dgx.view(B * L, 4 * H), xemb.view(B * L, E)).cpu()
+    assert (dw_ih - p[1].grad).abs().max() < 1e-4 * p[1].grad.abs().max().clamp_min(1)
+    assert (ops.colsum(dgx.view(B * L, 4 * H)).cpu() - p[3].grad).abs().max() < 1e-4
