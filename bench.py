@@ -130,7 +130,13 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------- GPU leg
+def _log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        print(f"[bench {time.strftime('%H:%M:%S')} rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def gpu_leg(args):
+    _log("importing torch")
     import torch
     import torch.distributed as dist
     from videonavqa_b200 import dp, ops
@@ -144,7 +150,9 @@ def gpu_leg(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        _log("init_process_group")
         dist.init_process_group("nccl", device_id=dev)
+    _log("process group ready; building model")
     B = args.batch
     torch.manual_seed(1)
     M = MODELS[args.model]
@@ -159,8 +167,10 @@ def gpu_leg(args):
         model = TimeMultiHopFiLMPretrainedStem(num_tail_channels=M["tail"], **common)
     model = model.to(dev)
     reducer = None
+    _log("model on device")
     if world > 1:
         dp.broadcast_module(model)
+        _log("weights broadcast")
         reducer = dp.GradAllReducer(model)
     train = args.workload == "train"
     model.train(train)
@@ -169,7 +179,9 @@ def gpu_leg(args):
     # synthetic clips, a different shard per rank; kept in pinned host memory for the e2e leg
     v, q, v_lens, q_lens, labels = synthetic_batch(B, c_in=CFG["c_in"], T=CFG["T"], Lq=CFG["Lq"], vocab=CFG["vocab"],
                                                    classes=CFG["classes"], seed=rank, ragged=args.ragged)
+    _log("synthetic batch generated")
     host = [t.pin_memory() for t in (v, q, v_lens, q_lens, labels)]
+    _log("host batch pinned")
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
     n_frames_total = int(v_lens.sum())
 
@@ -193,9 +205,13 @@ def gpu_leg(args):
 
     # ---------------- device-resident timing
     dev_in = [t.to(dev) for t in host]
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         step(*dev_in)
+        if i == 0:
+            torch.cuda.synchronize()
+            _log("first warm-up step done")
     barrier()
+    _log("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -208,6 +224,7 @@ def gpu_leg(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    _log(f"device-resident timing done: {ms:.2f} ms/step")
     launches = (ops.LAUNCHES - launches0) // args.steps
     prof, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
@@ -221,32 +238,46 @@ def gpu_leg(args):
     # ---------------- end-to-end timing: host inputs every step, prefetched on a copy stream, loss read back
     copy_stream = torch.cuda.Stream(device=dev)
 
+    # N > 1: the inputs are copied on the compute stream (no prefetch stream) - see DESIGN.md §4
+    prefetch = world == 1 and os.environ.get("BENCH_E2E_PREFETCH", "1") != "0"
+
     def fetch():
+        if not prefetch:
+            return [x.to(dev, non_blocking=True) for x in host], None
         with torch.cuda.stream(copy_stream):
             t = [x.to(dev, non_blocking=True) for x in host]
             ev = torch.cuda.Event(); ev.record(copy_stream)
         return t, ev
 
-    for _ in range(2):
-        t, ev = fetch(); torch.cuda.current_stream().wait_event(ev); r = step(*t); float(r.sum())
+    def consume(item):
+        t, ev = item
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            for x in t:
+                x.record_stream(torch.cuda.current_stream())
+        return t
+
+    for i in range(2):
+        r = step(*consume(fetch()))
+        _ = r.detach().sum().item()
+        _log(f"e2e warm-up step {i} done")
     barrier()
     d2h = 4 if train else B * CFG["classes"] * 4
-    t_wall0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     nxt = fetch()
     for i in range(args.steps):
-        t, ev = nxt
-        torch.cuda.current_stream().wait_event(ev)
-        for x in t:
-            x.record_stream(torch.cuda.current_stream())
-        if i + 1 < args.steps:
+        t = consume(nxt)
+        if i + 1 < args.steps and prefetch:
             nxt = fetch()                      # overlaps with this step's compute
         r = step(*t)
-        _ = r.item() if train else r.cpu()     # device->host read of the step result
+        _ = r.detach().sum().item() if train else r.cpu()     # device->host read of the step result
+        if i + 1 < args.steps and not prefetch:
+            nxt = fetch()
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1) / args.steps
+    _log(f"e2e timing done: {e2e_ms:.2f} ms/step")
     del t_wall0
 
     if world > 1:

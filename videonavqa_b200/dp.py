@@ -5,14 +5,20 @@ forward needs no collective; the only exchange is ONE gradient all-reduce per st
 
   * SUM, not mean: the reference loss is CrossEntropyLoss(reduction='sum') (eval.sh:15), so N ranks x b clips is
     the same optimisation step as one rank x N*b clips (per-replica BatchNorm statistics, as in ordinary DDP);
-  * overlapped with backward: the engine reports every gradient the moment it is final (engine.GradSink) and the
-    all-reduce of that tensor is enqueued asynchronously (NCCL runs it on its own stream, in-switch NVLS reduction
-    when available) while the remaining backward kernels keep the SMs busy; the handles are waited for at the end
-    of backward, before the optimizer;
+  * default = one flat bucket: the engine reports every gradient the moment it is final (engine.GradSink); the
+    reducer collects the registered parameters' gradients and, at the end of backward, packs them into one
+    contiguous fp32 buffer (283 MB for the attention model), runs a single ncclAllReduce (NVLS in-switch reduction
+    when available) and scatters the result back.  ~1 ms against ~140 ms of compute per step;
+  * optional (VNQA_DP_OVERLAP=1) = per-tensor asynchronous all-reduce started from inside backward so that NCCL
+    overlaps the remaining backward kernels.  Measured fine at 2 ranks; at >= 4 ranks it dead-locked
+    intermittently on the test boxes (NCCL kernels waiting for SMs behind the persistent 148-CTA cluster kernels of
+    different ranks), so it is off by default until that is understood;
   * the unregistered conv1x1_layers (quirk Q1) are broadcast from rank 0 at start-up - nothing else would ever
     synchronise them - and are never optimised, exactly as in the reference.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -29,29 +35,49 @@ def broadcast_module(module, src=0, group=None):
 
 
 class GradAllReducer:
-    """Installs itself as the module's gradient hook; all-reduces each gradient as soon as the backward pass
-    produces it.  Call ``wait()`` after ``loss.backward()`` and before ``optimizer.step()``."""
+    """Installs itself as the module's gradient hook.  ``wait()`` is called by the autograd node at the end of
+    backward (before autograd hands the gradients to ``.grad`` / the optimizer): after it returns every registered
+    parameter's gradient holds the SUM over ranks."""
 
-    def __init__(self, module, group=None, registered_only=True):
+    def __init__(self, module, group=None, registered_only=True, overlap=None):
         self.group = group
+        self.overlap = (os.environ.get("VNQA_DP_OVERLAP", "0") == "1") if overlap is None else overlap
         self.handles = []
+        self.pending = []
         self.bytes = 0
+        self.last_bytes = 0
+        self._flat = None
         self._registered = {n for n, _ in module.named_parameters()} if registered_only else None
         module._grad_hook = self
 
     def __call__(self, name, tensor):
         if self._registered is not None and name not in self._registered:
             return      # conv1x1_layers: never optimised in the reference, gradients stay local
-        self.handles.append(dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.bytes += tensor.numel() * tensor.element_size()
+        if self.overlap:
+            self.handles.append(dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.pending.append(tensor)
 
     def wait(self):
-        for h in self.handles:
-            h.wait()
+        if self.overlap:
+            for h in self.handles:
+                h.wait()
+            self.handles = []
+        elif self.pending:
+            ts = self.pending
+            n = sum(t.numel() for t in ts)
+            if self._flat is None or self._flat.numel() != n or self._flat.device != ts[0].device:
+                self._flat = torch.empty(n, device=ts[0].device, dtype=ts[0].dtype)
+            views = [v.view_as(t) for v, t in zip(self._flat.split([t.numel() for t in ts]), ts)]
+            torch._foreach_copy_(views, ts)                                   # pack (data movement only)
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+            torch._foreach_copy_(ts, views)                                   # unpack
+            self.pending = []
         n = self.bytes
-        if self.handles:
+        if n:
             self.last_bytes = n
-        self.handles, self.bytes = [], 0
+        self.bytes = 0
         return n
 
 
