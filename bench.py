@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--model", choices=list(MODELS), default="attn", help="attn = the headline metric")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU")
     ap.add_argument("--ragged", action="store_true", help="ragged v_lens (secondary config) instead of all 35")
-    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU sample")
+    ap.add_argument("--cpu-clips", type=int, default=4, help="clips in the bounded CPU sample (~10 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -314,6 +314,10 @@ def gpu_leg(args):
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<EPI_FILM> (conv3x3 1024->1024 + FiLM/ReLU/residual)",
                 "achieved": k["tflops"], "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                 "frac": round(k["tflops"] / tf32_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "peak_nominal": 1100.0, "frac_nominal": round(k["tflops"] / 1100.0, 4),
+                "note": "frac > 1: cuBLAS bf16 sustains 61% of its nominal rate under the 1 kW cap, this tf32 kernel "
+                        "keeps the tensor pipe 96% busy (profiles/r01b_conv3x3_film_2cta.ncu_details.txt); "
+                        "frac_nominal is against the 1.1 PFLOP/s dense tf32 datasheet figure",
                 "flops_per_launch": klass[dom_tag][2], "ms_per_launch": k["ms_per_launch"]}
     clips = B * world
     gflop = M["train_gflop"] if train else M["fwd_gflop"]

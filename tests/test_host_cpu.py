@@ -136,3 +136,34 @@ def test_product_never_imports_the_oracle():
     for f in glob.glob(os.path.join(ROOT, "videonavqa_b200", "**", "*.py"), recursive=True):
         src = open(f).read()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_dropin_models_package_shim():
+    """With dropin/ first on the path the reference drivers' imports resolve to the B200 classes."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    try:
+        a = importlib.import_module("models.film_attn_pt_stem")
+        g = importlib.import_module("models.film_global_pooling_pt_stem")
+        t = importlib.import_module("models.time_multi_hop_pt_stem")
+        import videonavqa_b200.models as real
+        assert a.FiLMAttnPretrainedStem is real.FiLMAttnPretrainedStem
+        assert g.FiLMGlobalPoolingPretrainedStem is real.FiLMGlobalPoolingPretrainedStem
+        assert t.TimeMultiHopFiLMPretrainedStem is real.TimeMultiHopFiLMPretrainedStem
+    finally:
+        sys.path.remove(os.path.join(ROOT, "dropin"))
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_constructor_validates_kernel_constraints():
+    from videonavqa_b200.models import FiLMAttnPretrainedStem
+    with pytest.raises(ValueError, match="multiples of 32"):
+        FiLMAttnPretrainedStem(2, 16, 7, num_input_channels=48, num_res_block_channels=50)
+    with pytest.raises(ValueError, match="hidden_size"):
+        FiLMAttnPretrainedStem(2, 16, 7, num_input_channels=32, num_res_block_channels=32, hidden_size=100)
+    with pytest.raises(NotImplementedError):
+        FiLMAttnPretrainedStem(2, 16, 7, num_input_channels=32, num_res_block_channels=32, q_encoder="bow")

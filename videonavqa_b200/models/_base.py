@@ -47,6 +47,16 @@ class _FilmFunction(torch.autograd.Function):
         return (None,) * 6 + tuple(grads.get(n) for n in mod._param_names)
 
 
+def check_channels(num_input_channels, num_res_block_channels, hidden_size):
+    """The tensor-core kernels stage operands in 32-channel TMA boxes and the recurrent kernels are instantiated for
+    hidden sizes 32 / 64 / 128 (every configuration the reference ships: 512 -> 512/1024 channels, hidden 128)."""
+    if num_input_channels % 32 or num_res_block_channels % 32:
+        raise ValueError("videonavqa_b200 needs num_input_channels and num_res_block_channels to be multiples of 32 "
+                         f"(got {num_input_channels}, {num_res_block_channels})")
+    if hidden_size not in (32, 64, 128):
+        raise ValueError(f"videonavqa_b200 supports hidden_size 32, 64 or 128 (got {hidden_size})")
+
+
 class FilmModuleBase(nn.Module):
     """Behaviour common to FiLMAttnPretrainedStem / FiLMGlobalPoolingPretrainedStem (and the multi-hop variant)."""
 

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine
-from ._base import FilmModuleBase, reference_init
+from ._base import FilmModuleBase, check_channels, reference_init
 
 
 class FiLMAttnPretrainedStem(FilmModuleBase):
@@ -17,6 +17,9 @@ class FiLMAttnPretrainedStem(FilmModuleBase):
                  num_res_block_channels=512, num_res_blocks=1, hidden_size=128, at_hidden_size=128,
                  max_num_frames=35, q_encoder='lstm', vocab_size=134):
         super().__init__()
+        check_channels(num_input_channels, num_res_block_channels, hidden_size)
+        if at_hidden_size % 32 or not 32 <= at_hidden_size <= 256:
+            raise ValueError(f"videonavqa_b200 supports at_hidden_size in 32..256, multiple of 32 (got {at_hidden_size})")
         assert q_encoder.lower() in ['lstm', 'bow'], "Invalid question encoder! ('lstm', 'bow')"
         if q_encoder.lower() != 'lstm':
             # the reference's 'bow' branch discards its own averaging and hard-codes

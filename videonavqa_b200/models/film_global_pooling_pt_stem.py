@@ -3,7 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine
-from ._base import FilmModuleBase, reference_init
+from ._base import FilmModuleBase, check_channels, reference_init
 
 
 class FiLMGlobalPoolingPretrainedStem(FilmModuleBase):
@@ -13,6 +13,7 @@ class FiLMGlobalPoolingPretrainedStem(FilmModuleBase):
                  num_res_block_channels=512, num_tail_channels=16, num_res_blocks=1, hidden_size=128,
                  q_encoder='lstm', vocab_size=134):
         super().__init__()
+        check_channels(num_input_channels, num_res_block_channels, hidden_size)
         assert q_encoder.lower() in ['lstm', 'bow'], "Invalid question encoder! ('lstm', 'bow')"
         if q_encoder.lower() != 'lstm':
             raise NotImplementedError("q_encoder='bow' is not supported by the B200 path; use 'lstm'")

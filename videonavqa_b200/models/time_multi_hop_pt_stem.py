@@ -3,7 +3,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine
-from ._base import FilmModuleBase, reference_init
+from ._base import FilmModuleBase, check_channels, reference_init
 
 
 class TimeMultiHopFiLMPretrainedStem(FilmModuleBase):
@@ -13,6 +13,7 @@ class TimeMultiHopFiLMPretrainedStem(FilmModuleBase):
                  num_res_block_channels=512, num_res_blocks=1, num_tail_channels=32, hidden_size=128,
                  vocab_size=134):
         super().__init__()
+        check_channels(num_input_channels, num_res_block_channels, hidden_size)
         self.nb_classes = nb_classes
         self.batch_size = batch_size
         self.q_embedding_size = q_embedding_size
