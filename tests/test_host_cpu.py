@@ -167,3 +167,20 @@ def test_constructor_validates_kernel_constraints():
         FiLMAttnPretrainedStem(2, 16, 7, num_input_channels=32, num_res_block_channels=32, hidden_size=100)
     with pytest.raises(NotImplementedError):
         FiLMAttnPretrainedStem(2, 16, 7, num_input_channels=32, num_res_block_channels=32, q_encoder="bow")
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (CPU oracle on a bounded sample) prints ONE JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-clips", "1", "--workload", "eval"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["vs_baseline"] is None
