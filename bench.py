@@ -278,7 +278,6 @@ def gpu_leg(args):
     barrier()
     e2e_ms = f0.elapsed_time(f1) / args.steps
     _log(f"e2e timing done: {e2e_ms:.2f} ms/step")
-    del t_wall0
 
     if world > 1:
         tt = torch.tensor([ms, e2e_ms], device=dev)
