@@ -225,3 +225,33 @@ def test_clip_independence_full_batch():
         b_ = m(v2, q2, v_lens, ql2)
     assert torch.equal(a[0], b_[0])
     assert torch.isfinite(a).all()
+
+
+def test_training_steps_reduce_the_loss():
+    """Size-independent property of the whole fwd+bwd path: a few Adam steps on one fixed batch lower the summed
+    cross-entropy (gradients point downhill), for all three models."""
+    from videonavqa_b200.models import (FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem,
+                                        TimeMultiHopFiLMPretrainedStem)
+    B = 4
+    v, q, _, q_lens, labels = O.synthetic_batch(B, c_in=64, vocab=30, classes=5, seed=21, Lq=16, q_len_range=(3, 16))
+    v_lens = torch.tensor([35, 22, 22, 6])
+    common = dict(batch_size=B, q_embedding_size=32, nb_classes=5, num_input_channels=64, num_res_block_channels=128,
+                  num_res_blocks=2, hidden_size=64, vocab_size=30)
+    for ctor in (lambda: FiLMAttnPretrainedStem(at_hidden_size=64, **common),
+                 lambda: FiLMGlobalPoolingPretrainedStem(num_tail_channels=16, **common),
+                 lambda: TimeMultiHopFiLMPretrainedStem(num_tail_channels=16, **common)):
+        torch.manual_seed(0)
+        m = ctor().cuda().train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        losses = []
+        for _ in range(6):
+            m.init_hidden()
+            out = m(v.cuda(), q.cuda(), v_lens.cuda(), q_lens.cuda())
+            loss = torch.nn.functional.cross_entropy(out, labels.cuda(), reduction="sum")
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+            losses.append(loss.item())
+        assert all(map(lambda x: x == x and abs(x) < 1e6, losses)), losses
+        assert losses[-1] < losses[0], (type(m).__name__, losses)

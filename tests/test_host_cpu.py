@@ -184,3 +184,22 @@ def test_bench_reference_arm_json_contract():
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["vs_baseline"] is None
+
+
+def test_header_is_valid_c_and_struct_matches_ctypes(tmp_path):
+    """include/vnqa_b200.h must compile as plain C (the ABI has no C++ / torch types) and vnqa_conv_args must have
+    the size and field offsets the ctypes mirror assumes."""
+    import ctypes
+    import subprocess
+    from videonavqa_b200._lib import ConvArgs
+    src = tmp_path / "abi.c"
+    fields = [f[0] for f in ConvArgs._fields_]
+    body = "\n".join(f'  printf("%zu\\n", offsetof(vnqa_conv_args, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vnqa_b200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(vnqa_conv_args));\n' + body + "\n  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(ConvArgs)
+    assert out[1:] == [getattr(ConvArgs, f).offset for f in fields]
