@@ -130,6 +130,35 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------- GPU leg
+def summarise_kernels(klass, steps, ms_per_step):
+    """klass: tag -> [total_ms, launches, work per launch] (flops, or bytes for tags starting with 'hbm.')."""
+    out = {}
+    for tag, (tot, n, work) in sorted(klass.items(), key=lambda kv: -kv[1][0]):
+        if n == 0 or tot <= 0:
+            continue
+        e = {"launches_per_step": n // max(steps, 1), "ms_per_launch": round(tot / n, 4),
+             "share_of_step": round(tot / max(steps, 1) / ms_per_step, 4)}
+        if tag.startswith("hbm."):
+            e["gb_per_s"] = round(work / (tot / n) * 1e-6, 1)
+        else:
+            e["tflops"] = round(work / (tot / n) * 1e-9, 1)
+        out[tag] = e
+    return out
+
+
+def hbm_roofline(kernels, peaks):
+    """HBM roofline entry for the FiLM-backward streaming kernel (reads dOut and z, writes dz: 3 activation tensors)."""
+    try:
+        k = kernels["hbm.film_bwd"]
+        peak = float(peaks.get("hbm_gbs") or 6650.0)
+        return {"bound": "hbm", "kernel": "film_bwd_kernel (autograd of the FiLM modulation, 3 x 1.19 GB per launch)",
+                "achieved": k["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": round(k["gb_per_s"] / peak, 4),
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else
+                "fallback 6.65 TB/s (B200_PROFILING.md)"}
+    except Exception:
+        return None
+
+
 def _log(msg):
     if os.environ.get("BENCH_VERBOSE"):
         print(f"[bench {time.strftime('%H:%M:%S')} rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
@@ -298,10 +327,7 @@ def gpu_leg(args):
                 if peaks else "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)")
     tf32_peak = bf16_peak / 2.0
     dom_tag = f"conv_gemm.9tap.epi3.k{CFG['C']}.n{CFG['C']}"            # conv3x3 + FiLM epilogue (forward)
-    kernels = {}
-    for tag, (tot, n, flops) in sorted(klass.items(), key=lambda kv: -kv[1][0]):
-        kernels[tag] = {"launches_per_step": n // args.steps, "ms_per_launch": round(tot / n, 4),
-                        "tflops": round(flops / (tot / n) * 1e-9, 1), "share_of_step": round(tot / args.steps / ms, 4)}
+    kernels = summarise_kernels(klass, args.steps, ms)
     roof = None
     if dom_tag in kernels:
         k = kernels[dom_tag]
@@ -340,6 +366,7 @@ def gpu_leg(args):
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": roof,
+        "roofline_hbm": hbm_roofline(kernels, peaks),
         "kernels": kernels,
     }
     if reducer is not None:

@@ -203,3 +203,18 @@ def test_header_is_valid_c_and_struct_matches_ctypes(tmp_path):
     out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert out[0] == ctypes.sizeof(ConvArgs)
     assert out[1:] == [getattr(ConvArgs, f).offset for f in fields]
+
+
+def test_bench_kernel_summary_helpers():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    klass = {"conv_gemm.9tap.epi3.k1024.n1024": [62.0, 10, 5.496e12], "hbm.film_bwd": [5.5, 10, 3.578e9],
+             "empty": [0.0, 0, 1.0]}
+    k = bench.summarise_kernels(klass, steps=2, ms_per_step=140.0)
+    assert abs(k["conv_gemm.9tap.epi3.k1024.n1024"]["tflops"] - 886.5) < 1 and "empty" not in k
+    assert abs(k["hbm.film_bwd"]["gb_per_s"] - 6505.5) < 1 and k["hbm.film_bwd"]["launches_per_step"] == 5
+    r = bench.hbm_roofline(k, {"hbm_gbs": 6547.8})
+    assert r["bound"] == "hbm" and 0.98 < r["frac"] < 1.0
+    assert bench.hbm_roofline({}, {}) is None

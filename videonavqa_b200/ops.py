@@ -202,7 +202,9 @@ def bn_eval_affine(gamma, beta, running_mean, running_var, eps):
 def bn_apply(y, img_frame, scale, shift):
     n_img, _, C = y.shape
     x = torch.empty_like(y)
-    check(_lib.lib().vnqa_bn_apply(_p(y), _p(x), _p(img_frame), _p(scale), _p(shift), n_img, C, _stream()), "bn_apply")
+    with _timed("hbm.bn_apply", 2.0 * y.numel() * 4):
+        check(_lib.lib().vnqa_bn_apply(_p(y), _p(x), _p(img_frame), _p(scale), _p(shift), n_img, C, _stream()),
+              "bn_apply")
     return x
 
 
@@ -220,8 +222,10 @@ def bn_backward(dx, y, img_frame, frame_ct, n_frames, mean, rstd, gamma, dbias, 
 def film_backward(dout, z, film, film_row, alpha_off, dfilm, dbias, mask_relu=True):
     n_img, _, C = z.shape
     dz = torch.empty_like(z)
-    check(_lib.lib().vnqa_film_backward(_p(dout), _p(z), _p(film), _p(film_row), film.stride(0), alpha_off, n_img, C,
-                                        _p(dz), _p(dfilm), _p(dbias), int(mask_relu), _stream()), "film_backward")
+    with _timed("hbm.film_bwd", 3.0 * z.numel() * 4):
+        check(_lib.lib().vnqa_film_backward(_p(dout), _p(z), _p(film), _p(film_row), film.stride(0), alpha_off, n_img,
+                                            C, _p(dz), _p(dfilm), _p(dbias), int(mask_relu), _stream()),
+              "film_backward")
     return dz
 
 
