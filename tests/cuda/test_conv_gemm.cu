@@ -319,6 +319,8 @@ int main(int argc, char** argv) {
       {"conv3x3_dgrad_res", 9, 128, 128, 10, 0, 1, VNQA_EPI_DGRAD_RES, 0, 0},
       {"flat_splitk_partial", 1, 832, 128, 300, 1, 5, VNQA_EPI_PARTIAL, 0, 0},
       {"flat_plain_tail", 1, 128, 4160, 77, 1, 1, VNQA_EPI_PLAIN, 0, 0},
+      {"flat_plain_cta_pair", 1, 128, 512, 300, 1, 1, VNQA_EPI_PLAIN, 0, 0},
+      {"conv3x3_film_cta_pair_ragged", 9, 64, 256, 21, 0, 1, VNQA_EPI_FILM, 0, 0},
       {"many_tiles_persistent", 9, 64, 512, 400, 0, 1, VNQA_EPI_FILM, 20000, 0},
   };
   if (perf) {
