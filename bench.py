@@ -19,6 +19,7 @@ clip_grad_norm + Adam, exactly the reference's loop body (eval/q_and_v_eval.py:1
 --impl reference: only the CPU leg, as its own JSON line.
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -164,6 +165,34 @@ def _log(msg):
         print(f"[bench {time.strftime('%H:%M:%S')} rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
+def metric_name(args):
+    mname = {"attn": "FiLM-attn", "gp": "FiLM-gp", "tmh": "time-multi-hop"}[args.model]
+    return f"video-QA clips/sec ({mname} fwd+bwd)" if args.workload == "train" \
+        else f"video-QA clips/sec ({mname} eval forward)"
+
+
+def workload_name(args):
+    """The same string on both arms (b200 and reference): the configuration BASELINE.json's metric is quoted on."""
+    M = MODELS[args.model]
+    return (f"{M['name']} {args.workload} step, eval.sh hyper-parameters (C_in 512, C 1024, {M['nb']} blocks, hidden 128, "
+            f"70 classes), {args.batch} clips/GPU x 35 frames x 512x10x13"
+            + (", ragged v_lens" if args.ragged else ", all clips 35 frames"))
+
+
+def start_watchdog():
+    """Host-side dead-man switch: a wedged collective or kernel must not hold the GPU box until the caller's limit."""
+    limit = float(os.environ.get("BENCH_WATCHDOG_S", "1500"))
+    if limit <= 0:
+        return
+
+    def bite():
+        print(f"bench.py: watchdog - no result after {limit:.0f} s, aborting", file=sys.stderr, flush=True)
+        os._exit(3)
+    t = threading.Timer(limit, bite)
+    t.daemon = True
+    t.start()
+
+
 def gpu_leg(args):
     _log("importing torch")
     import torch
@@ -180,7 +209,9 @@ def gpu_leg(args):
     dev = torch.device("cuda", local)
     if world > 1:
         _log("init_process_group")
-        dist.init_process_group("nccl", device_id=dev)
+        # a lost rank must end the job with an error, not hang the box: NCCL's watchdog aborts after the timeout
+        dist.init_process_group("nccl", device_id=dev,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("BENCH_NCCL_TIMEOUT_S", "240"))))
     _log("process group ready; building model")
     B = args.batch
     torch.manual_seed(1)
@@ -346,16 +377,13 @@ def gpu_leg(args):
                 "flops_per_launch": klass[dom_tag][2], "ms_per_launch": k["ms_per_launch"]}
     clips = B * world
     gflop = M["train_gflop"] if train else M["fwd_gflop"]
-    mname = {"attn": "FiLM-attn", "gp": "FiLM-gp", "tmh": "time-multi-hop"}[args.model]
     scale = n_frames_total / (B * CFG["T"])
     out = {
-        "metric": f"video-QA clips/sec ({mname} fwd+bwd)" if train else f"video-QA clips/sec ({mname} eval forward)",
+        "metric": metric_name(args),
         "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32 operands, fp32 accumulate/storage", "data": "synthetic",
-        "config": {"workload": f"{M['name']} {args.workload} step, eval.sh hyper-parameters (C_in 512, C 1024, {M['nb']} blocks,"
-                               f" hidden 128, 70 classes), {B} clips/GPU x 35 frames x 512x10x13"
-                               + (", ragged v_lens" if args.ragged else ", all clips 35 frames"),
+        "config": {"workload": workload_name(args),
                    "global_batch": clips, "frames_per_clip": CFG["T"], "parallelism": f"dp{world}",
                    "step": "fwd+CE(sum)+bwd" + ("+allreduce(sum)" if world > 1 else "") + "+clip_grad_norm+Adam" if train
                    else "eval forward", "l2": "inputs larger than L2 (v_input 596 MB, activations 1.19 GB each)",
@@ -379,19 +407,20 @@ def gpu_leg(args):
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
+    start_watchdog()
     if args.impl == "reference":
         if rank != 0:
             return
         iters = max(1, min(args.steps, 3))
         cb = cpu_leg(args.workload, args.cpu_clips, iters=iters, warm=min(args.warmup, 1), kind=args.model)
         line = {"impl": "reference",
-                "metric": "video-QA clips/sec (FiLM-attn fwd+bwd)" if args.workload == "train"
-                else "video-QA clips/sec (FiLM-attn eval forward)",
+                "metric": metric_name(args),
                 "value": round(cb["value"], 4), "unit": "clips/s", "n_gpus": args.gpus, "steps": iters,
                 "warmup": min(args.warmup, 1), "ms_per_step": round(cb["sec_per_step"] * 1e3, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                "config": {"workload": f"film_attn_pt {args.workload} step, eval.sh hyper-parameters; CPU oracle "
-                                       f"(port of the reference) on a bounded sample of {args.cpu_clips} clips x 35 frames"},
+                "config": {"workload": workload_name(args),
+                           "sample": f"CPU oracle (port of the reference), each step a bounded sample of "
+                                     f"{args.cpu_clips} clips x 35 frames of that workload"},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": round(cb["value"], 4), "unit": "clips/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
