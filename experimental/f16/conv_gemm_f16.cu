@@ -1,0 +1,581 @@
+// CANDIDATE (not yet run on hardware): fp16-operand variant of videonavqa_b200/csrc/conv_gemm.cu.
+//
+// Same pipeline, same tile geometry IN BYTES: a 128-byte swizzle row now holds 64 fp16 reduction elements instead of
+// 32 fp32, one tcgen05.mma.kind::f16 consumes 32 bytes = 16 elements of it, so every smem stage carries twice the
+// reduction depth for the same bytes and the same four MMAs - the K loop is half as long and each MMA issues at the
+// full fp16 rate.  Operand precision is unchanged (fp16 and tf32 both keep 10 mantissa bits), accumulation is fp32
+// in TMEM.  Replaces nn.Conv2d 3x3 / 1x1 (+ fused bias / ReLU / BN affine / FiLM / residual) of
+// models/film_attn_pt_stem.py:211,219,224-241, the Linear of :244 and their data gradients.
+//
+//   D[co][pix] = sum_{tap, ci} Wp[tap][co][ci] * X[pix (+) tap][ci]
+//
+// M = output channels (128 TMEM lanes, 256 for a CTA pair), N = 208 pixels = 8 images x 2 rows x 13; the pixel block
+// of a filter tap is the 4-D TMA box {64 ch, 13, 2, images} and the halo is the TMA out-of-bounds zero fill.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue; double-buffered accumulators;
+// persistent CTAs.  Activations are stored fp16 ([img][130][C]); BatchNorm input (STATS) and split-K partials
+// stay fp32.
+#include <cstdlib>
+
+#include <cuda_fp16.h>
+
+#include "../../videonavqa_b200/csrc/common.h"
+#include "../../videonavqa_b200/csrc/ptx.cuh"
+#include "f16_common.cuh"
+
+namespace vnqa {
+namespace f16 {
+
+constexpr int BM = 128;            // output channels per CTA tile (TMEM lanes)
+constexpr int BN = 208;            // pixels per tile (TMEM columns) = 8 * 2 * 13
+constexpr int BK = 64;             // fp16 reduction elements per stage = one 128-byte swizzle row
+constexpr int UMMA_K = 16;         // kind::f16: 32 bytes per instruction
+constexpr int A_BYTES = BM * BK * 2;           // 16384
+constexpr int ACC_COLS = 256;                  // TMEM column stride between the two accumulator stages
+constexpr int TMEM_COLS = 512;
+constexpr int IMG_PER_TILE = 8;
+constexpr int ROWS_PER_IMG_TILE = 26;          // 2 image rows x 13
+constexpr int NUM_THREADS = 256;
+
+template <int NCTA>
+struct Cfg {
+  static constexpr int B_ROWS = BN / NCTA;                 // pixel rows staged per CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;          // 26624 / 13312 (multiples of 1024)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 43008 / 29696
+  static constexpr int STAGES = NCTA == 1 ? 5 : 7;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct KParams {
+  int taps, k_chunks, m_tiles, n_tiles, splits, rows_pad, flat, cout, n_img;
+  int out_f32;                 // BIAS_RELU / PLAIN only: store fp32 (tensors that leave the fp16 domain)
+  long long out_split_stride;  // PARTIAL: n_img * cout
+  void* out;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const int* img_frame;
+  double* stat_sum;
+  double* stat_sq;
+  const float* film;
+  const int* film_row;
+  int film_ld, alpha_off;
+  const __half* res;
+  __half* z_out;
+  const __half* add;
+  float* dbias;
+  float grad_unscale;
+};
+
+struct TileCoord {
+  int mt, nt, sp;
+};
+// items enumerate (m-tile group, n-tile, split), m fastest: co-resident CTAs share activation tiles in L2
+template <int NCTA>
+__device__ __forceinline__ TileCoord decode_tile(int item, const KParams& p, int rank) {
+  const int mg = p.m_tiles / NCTA;
+  TileCoord t;
+  t.mt = (item % mg) * NCTA + rank;
+  const int r = item / mg;
+  t.nt = r % p.n_tiles;
+  t.sp = r / p.n_tiles;
+  return t;
+}
+
+__device__ __forceinline__ float ldh(const __half* p) { return __half2float(__ldg(p)); }
+
+// ------------------------------------------------------------------------------------------------ epilogue
+// One accumulator tile (128 channels x 208 pixels) from TMEM to global memory; thread = output channel.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord& tc, uint32_t t_base, int ew,
+                                              int lane) {
+  constexpr bool kF32Out = EPI == VNQA_EPI_BIAS_RELU_STATS || EPI == VNQA_EPI_PARTIAL;
+  const int co = tc.mt * BM + ew * 32 + lane;
+  const bool co_ok = co < p.cout;
+  float bias = 0.f, scale = 1.f, shift = 0.f;
+  if (EPI == VNQA_EPI_BIAS_RELU || EPI == VNQA_EPI_BIAS_RELU_AFFINE || EPI == VNQA_EPI_BIAS_RELU_STATS ||
+      EPI == VNQA_EPI_FILM) {
+    if (co_ok) bias = __ldg(p.bias + co);
+  }
+  if (EPI == VNQA_EPI_BIAS_RELU_AFFINE && co_ok) {
+    scale = __ldg(p.scale + co);
+    shift = __ldg(p.shift + co);
+  }
+  float* out32 = reinterpret_cast<float*>(p.out);
+  __half* out16 = reinterpret_cast<__half*>(p.out);
+  if (EPI == VNQA_EPI_PARTIAL) out32 += (long long)tc.sp * p.out_split_stride;
+
+  double st_sum = 0.0, st_sq = 0.0;  // STATS: running per-frame accumulators
+  int st_frame = -1;
+  float db_acc = 0.f;                // DGRAD_RES: per-channel sum
+
+#pragma unroll 1
+  for (int nl = 0; nl < IMG_PER_TILE; ++nl) {
+    uint32_t v[ROWS_PER_IMG_TILE];
+    tmem_ld_x16(t_base + nl * ROWS_PER_IMG_TILE, v);
+    tmem_ld_x8(t_base + nl * ROWS_PER_IMG_TILE + 16, v + 16);
+    tmem_ld_x2(t_base + nl * ROWS_PER_IMG_TILE + 24, v + 24);
+    tmem_ld_wait();
+
+    long long row0;  // first output row of this 26-column group
+    int nvalid;      // valid rows in the group
+    int img = 0;
+    if (p.flat) {
+      row0 = (long long)tc.nt * BN + nl * ROWS_PER_IMG_TILE;
+      long long rem = (long long)p.n_img - row0;
+      nvalid = rem >= ROWS_PER_IMG_TILE ? ROWS_PER_IMG_TILE : (rem > 0 ? (int)rem : 0);
+    } else {
+      img = (tc.nt / 5) * IMG_PER_TILE + nl;
+      row0 = (long long)img * VNQA_IMG_PIX + (tc.nt % 5) * ROWS_PER_IMG_TILE;
+      nvalid = img < p.n_img ? ROWS_PER_IMG_TILE : 0;
+    }
+    if (nvalid > 0 && co_ok) {
+      const long long o0 = row0 * p.cout + co;
+      if (EPI == VNQA_EPI_BIAS_RELU) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) {
+            const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
+            if (p.out_f32) out32[o0 + (long long)r * p.cout] = y;
+            else out16[o0 + (long long)r * p.cout] = __float2half_rn(y);
+          }
+      } else if (EPI == VNQA_EPI_BIAS_RELU_AFFINE) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid)
+            out16[o0 + (long long)r * p.cout] =
+                __float2half_rn(fmaf(fmaxf(__uint_as_float(v[r]) + bias, 0.f), scale, shift));
+      } else if (EPI == VNQA_EPI_BIAS_RELU_STATS) {
+        const int fr = __ldg(p.img_frame + img);
+        if (fr != st_frame) {
+          if (st_frame >= 0) {
+            atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
+            atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
+          }
+          st_frame = fr; st_sum = 0.0; st_sq = 0.0;
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
+          out32[o0 + (long long)r * p.cout] = y;     // BatchNorm input stays fp32 (normalised by bn_apply)
+          s1 += y;
+          s2 = fmaf(y, y, s2);
+        }
+        st_sum += (double)s1;
+        st_sq += (double)s2;
+      } else if (EPI == VNQA_EPI_FILM) {
+        const float* frow = p.film + (long long)__ldg(p.film_row + img) * p.film_ld + p.alpha_off;
+        const float alpha = __ldg(frow + co);
+        const float beta = __ldg(frow + p.cout + co);
+        const __half* rrow = p.res + o0;
+        float rv[ROWS_PER_IMG_TILE];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) rv[r] = ldh(rrow + (long long)r * p.cout);
+        if (p.z_out != nullptr) {
+          __half* zrow = p.z_out + o0;
+#pragma unroll
+          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+            zrow[(long long)r * p.cout] = __float2half_rn(__uint_as_float(v[r]) + bias);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          const float z = __uint_as_float(v[r]) + bias;
+          out16[o0 + (long long)r * p.cout] = __float2half_rn(fmaxf(fmaf(alpha, z, beta), 0.f) + rv[r]);
+        }
+      } else if (EPI == VNQA_EPI_PARTIAL) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) out32[o0 + (long long)r * p.cout] = __uint_as_float(v[r]);
+      } else if (EPI == VNQA_EPI_PLAIN) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) {
+            if (p.out_f32) out32[o0 + (long long)r * p.cout] = __uint_as_float(v[r]);
+            else out16[o0 + (long long)r * p.cout] = __float2half_rn(__uint_as_float(v[r]));
+          }
+      } else if (EPI == VNQA_EPI_DGRAD_RES) {
+        const __half* arow = p.add + o0;
+        const __half* mrow = p.res + o0;
+        float av[ROWS_PER_IMG_TILE], mv[ROWS_PER_IMG_TILE];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          av[r] = ldh(arow + (long long)r * p.cout);
+          mv[r] = ldh(mrow + (long long)r * p.cout);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          const __half g = mv[r] > 0.f ? __float2half_rn(__uint_as_float(v[r]) + av[r]) : __half(0.f);
+          out16[o0 + (long long)r * p.cout] = g;
+          db_acc += __half2float(g);
+        }
+      }
+    }  // nvalid && co_ok
+    __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+  }
+  if (EPI == VNQA_EPI_BIAS_RELU_STATS && st_frame >= 0 && co_ok) {
+    atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
+    atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
+  }
+  if (EPI == VNQA_EPI_DGRAD_RES && p.dbias != nullptr && co_ok) atomicAdd(p.dbias + co, db_acc * p.grad_unscale);
+  (void)kF32Out;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int EPI, int NCTA>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const KParams p) {
+  using C = Cfg<NCTA>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* acc_full = empty_bar + C::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int total_items = (p.m_tiles / NCTA) * p.n_tiles * p.splits;
+  const int first_item = blockIdx.x / NCTA;
+  const int item_stride = gridDim.x / NCTA;
+  const int k_iters = p.taps * p.k_chunks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], NCTA);        // one producer arrival per CTA (+ the TMA byte count)
+      mbar_init(&empty_bar[i], 1);          // one (multicast) MMA commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4 * NCTA);   // one arrive per epilogue warp of every CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    if (NCTA == 2) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (every CTA)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = first_item; item < total_items; item += item_stride) {
+      const TileCoord tc = decode_tile<NCTA>(item, p, rank);
+      const int a_row0 = tc.mt * BM;
+      int b1, b2, b3;  // B box coordinates of dims 1..3 before the tap shift
+      if (p.flat) {
+        b1 = tc.nt * BN + rank * C::B_ROWS; b2 = 0; b3 = 0;
+      } else {
+        b1 = 0; b2 = (tc.nt % 5) * 2; b3 = (tc.nt / 5) * IMG_PER_TILE + rank * (IMG_PER_TILE / NCTA);
+      }
+      const int k_base = tc.sp * p.k_chunks * BK;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        int dy = 0, dx = 0;
+        if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + A_BYTES;
+            if (NCTA == 1) {
+              mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              tma_load_2d(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
+              tma_load_4d(&tmB, &full_bar[stage], sb, k_base + kc * BK, b1 + dx, b2 + dy, b3);
+            } else {
+              // both CTAs' bytes land on the leader's barrier; the peer adds its arrival remotely
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+              tma_load_2d_2sm(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
+              tma_load_4d_2sm(&tmB, &full_bar[stage], sb, k_base + kc * BK, b1 + dx, b2 + dy, b3);
+              if (!leader) mbar_arrive_remote(&full_bar[stage], 0);
+            }
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    constexpr uint32_t idesc = umma_idesc_f16(BM * NCTA, BN, 0, 0);
+    constexpr uint64_t dbase = umma_desc_base_sw128(16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = first_item; item < total_items; item += item_stride) {
+      mbar_wait(&acc_empty[as], aphase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase, 3);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t adesc = umma_desc(dbase, sa);
+          const uint64_t bdesc = umma_desc(dbase, sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (>>4 = 2) inside the 128-byte swizzle row
+            if (NCTA == 1) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          if (NCTA == 1) {
+            umma_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
+            if (it == k_iters - 1) umma_commit(&acc_full[as]);    // accumulator complete -> epilogue
+          } else {
+            umma_commit_2sm(&empty_bar[stage], 0x3);              // ... in both CTAs of the pair
+            if (it == k_iters - 1) umma_commit_2sm(&acc_full[as], 0x3);
+          }
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (every CTA, own TMEM half)
+    const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = first_item; item < total_items; item += item_stride) {
+      const TileCoord tc = decode_tile<NCTA>(item, p, rank);
+      mbar_wait(&acc_full[as], aphase, 4);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * ACC_COLS;
+      epilogue_tile<EPI>(p, tc, t_base, ew, lane);
+      // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&acc_empty[as]);
+        else mbar_arrive_remote(&acc_empty[as], 0);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's smem until the end
+  if (warp == 2) {
+    if (NCTA == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int EPI, int NCTA>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int sms, cudaStream_t st) {
+  auto kern = conv_gemm_f16_kernel<EPI, NCTA>;
+  constexpr int smem = Cfg<NCTA>::SMEM_BYTES;
+  VNQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int items = (kp.m_tiles / NCTA) * kp.n_tiles * kp.splits;
+  const int groups = sms / NCTA;
+  const int grid = (items < groups ? items : groups) * NCTA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = NCTA == 2 ? 1 : 0;
+  VNQA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, kp));
+  return 0;
+}
+
+template <int EPI>
+static int launch_any(int ncta, const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int sms,
+                      cudaStream_t st) {
+  return ncta == 2 ? launch<EPI, 2>(tmA, tmB, kp, sms, st) : launch<EPI, 1>(tmA, tmB, kp, sms, st);
+}
+
+// fp16 tensor map, 128-byte swizzle (16-byte atoms: valid for K-major and MN-major 16-bit operands), zero OOB fill
+int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return -3;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[5];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp16) failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return -3;
+  }
+  return 0;
+}
+
+// (Cout, Cin, taps) fp32 -> fp16 [tap][rows_pad][Cin], or the mirrored / transposed data-gradient operand
+__global__ void pack_conv_weight_h_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin,
+                                          int taps, int rows_pad, int transpose_flip) {
+  const long long K = transpose_flip ? cout : cin;
+  const long long total = (long long)taps * rows_pad * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long r2 = i / K;
+    const int row = (int)(r2 % rows_pad);
+    const int tap = (int)(r2 / rows_pad);
+    float val = 0.f;
+    if (!transpose_flip) {
+      if (row < cout) val = __ldg(w + ((long long)row * cin + k) * taps + tap);
+    } else {
+      if (row < cin) val = __ldg(w + ((long long)k * cin + row) * taps + (taps - 1 - tap));
+    }
+    out[i] = __float2half_rn(val);
+  }
+}
+
+__global__ void to_half_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(__ldg(in + i) * scale);
+}
+
+}  // namespace f16
+}  // namespace vnqa
+
+using namespace vnqa;
+using namespace vnqa::f16;
+
+extern "C" int vnqa_pack_conv_weight_h(const float* w, void* packed, int32_t cout, int32_t cin, int32_t taps,
+                                       int32_t rows_pad, int32_t transpose_flip, void* stream) {
+  VNQA_REQUIRE(w && packed, "vnqa_pack_conv_weight_h: null pointer");
+  VNQA_REQUIRE(taps == 1 || taps == 9, "vnqa_pack_conv_weight_h: taps must be 1 or 9");
+  VNQA_REQUIRE(rows_pad >= (transpose_flip ? cin : cout), "vnqa_pack_conv_weight_h: rows_pad too small");
+  const long long total = (long long)taps * rows_pad * (transpose_flip ? cout : cin);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  pack_conv_weight_h_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__half*>(packed), cout, cin,
+                                                                   taps, rows_pad, transpose_flip);
+  VNQA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vnqa_to_half(const float* in, void* out, int64_t n, float scale, void* stream) {
+  VNQA_REQUIRE(in && out && n >= 0, "vnqa_to_half: bad arguments");
+  if (n == 0) return 0;
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  to_half_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__half*>(out), n, scale);
+  VNQA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vnqa_conv_gemm_h(const vnqa_conv_args_h* a, void* stream) {
+  VNQA_REQUIRE(a != nullptr, "vnqa_conv_gemm_h: null args");
+  VNQA_REQUIRE(a->taps == 1 || a->taps == 9, "vnqa_conv_gemm_h: taps must be 1 or 9 (got %d)", a->taps);
+  // a reduction that is not a multiple of 64 is completed by the TMA out-of-bounds zero fill (both operands)
+  VNQA_REQUIRE(a->cin > 0 && a->cin % 8 == 0, "vnqa_conv_gemm_h: cin must be a positive multiple of 8 (got %d)", a->cin);
+  VNQA_REQUIRE(a->cout % 8 == 0, "vnqa_conv_gemm_h: cout must be a multiple of 8 (got %d)", a->cout);
+  VNQA_REQUIRE(a->rows_pad % BM == 0 && a->rows_pad >= a->cout, "vnqa_conv_gemm_h: rows_pad must be cout rounded up to %d", BM);
+  VNQA_REQUIRE(a->n_img > 0, "vnqa_conv_gemm_h: empty batch");
+  VNQA_REQUIRE(a->w_packed && a->x && a->out, "vnqa_conv_gemm_h: null operand");
+  const int splits = a->flat ? (a->splits > 0 ? a->splits : 1) : 1;
+  VNQA_REQUIRE(!(a->flat && a->taps != 1), "vnqa_conv_gemm_h: flat GEMM has one tap");
+  VNQA_REQUIRE(splits == 1 || a->cin % BK == 0, "vnqa_conv_gemm_h: split-K needs cin per split to be a multiple of %d", BK);
+  VNQA_REQUIRE(!a->out_f32 || a->epi == VNQA_EPI_BIAS_RELU || a->epi == VNQA_EPI_PLAIN,
+               "vnqa_conv_gemm_h: out_f32 is available for BIAS_RELU and PLAIN");
+
+  KParams kp{};
+  kp.taps = a->taps;
+  kp.k_chunks = (a->cin + BK - 1) / BK;
+  kp.out_f32 = a->out_f32;
+  kp.m_tiles = a->rows_pad / BM;
+  kp.n_tiles = a->flat ? (a->n_img + BN - 1) / BN : ((a->n_img + IMG_PER_TILE - 1) / IMG_PER_TILE) * 5;
+  kp.splits = splits;
+  kp.rows_pad = a->rows_pad;
+  kp.flat = a->flat;
+  kp.cout = a->cout;
+  kp.n_img = a->n_img;
+  kp.out_split_stride = (long long)a->n_img * a->cout;
+  kp.out = a->out; kp.bias = a->bias; kp.scale = a->scale; kp.shift = a->shift;
+  kp.img_frame = a->img_frame; kp.stat_sum = a->stat_sum; kp.stat_sq = a->stat_sq;
+  kp.film = a->film; kp.film_row = a->film_row; kp.film_ld = a->film_ld; kp.alpha_off = a->alpha_off;
+  kp.res = reinterpret_cast<const __half*>(a->res);
+  kp.z_out = reinterpret_cast<__half*>(a->z_out);
+  kp.add = reinterpret_cast<const __half*>(a->add);
+  kp.dbias = a->dbias;
+  kp.grad_unscale = a->grad_unscale == 0.f ? 1.f : a->grad_unscale;
+
+  // CTA pairs (cta_group::2) whenever the output channels split into an even number of 128-row tiles
+  int ncta = (kp.m_tiles % 2 == 0) ? 2 : 1;
+  if (const char* e = getenv("VNQA_CONV_NCTA")) ncta = (atoi(e) == 1 || kp.m_tiles % 2) ? 1 : 2;   // bring-up switch
+
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t ktot = a->flat ? (uint64_t)a->cin * splits : (uint64_t)a->cin;
+    const uint64_t dims[2] = {ktot, (uint64_t)a->taps * a->rows_pad};
+    const uint64_t strides[1] = {ktot * 2};
+    const uint32_t box[2] = {BK, BM};
+    if (make_tmap_f16(&tmA, a->w_packed, 2, dims, strides, box)) return -3;
+  }
+  if (a->flat) {
+    const uint64_t ld = a->x_ld > 0 ? (uint64_t)a->x_ld : (uint64_t)a->cin * splits;
+    VNQA_REQUIRE(ld >= (uint64_t)a->cin * splits && ld % 8 == 0, "vnqa_conv_gemm_h: bad x_ld");
+    const uint64_t dims[4] = {(uint64_t)a->cin * splits, (uint64_t)a->n_img, 1, 1};
+    const uint64_t strides[3] = {ld * 2, ld * 2 * (uint64_t)a->n_img, ld * 2 * (uint64_t)a->n_img};
+    const uint32_t box[4] = {BK, (uint32_t)(BN / ncta), 1, 1};
+    if (make_tmap_f16(&tmB, a->x, 4, dims, strides, box)) return -3;
+  } else {
+    const uint64_t c = (uint64_t)a->cin;
+    const uint64_t dims[4] = {c, VNQA_IMG_W, VNQA_IMG_H, (uint64_t)a->n_img};
+    const uint64_t strides[3] = {c * 2, c * 2 * VNQA_IMG_W, c * 2 * VNQA_IMG_PIX};
+    const uint32_t box[4] = {BK, VNQA_IMG_W, 2, (uint32_t)(IMG_PER_TILE / ncta)};
+    if (make_tmap_f16(&tmB, a->x, 4, dims, strides, box)) return -3;
+  }
+
+  int sms = vnqa_sm_count();
+  if (sms <= 0) return -2;
+  cudaStream_t st = as_stream(stream);
+  switch (a->epi) {
+    case VNQA_EPI_BIAS_RELU:
+      VNQA_REQUIRE(a->bias, "conv_gemm_h: BIAS_RELU needs bias");
+      return launch_any<VNQA_EPI_BIAS_RELU>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_BIAS_RELU_AFFINE:
+      VNQA_REQUIRE(a->bias && a->scale && a->shift, "conv_gemm_h: AFFINE needs bias/scale/shift");
+      return launch_any<VNQA_EPI_BIAS_RELU_AFFINE>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_BIAS_RELU_STATS:
+      VNQA_REQUIRE(!a->flat && a->bias && a->img_frame && a->stat_sum && a->stat_sq, "conv_gemm_h: STATS operands");
+      return launch_any<VNQA_EPI_BIAS_RELU_STATS>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_FILM:
+      VNQA_REQUIRE(!a->flat && a->bias && a->film && a->film_row && a->res, "conv_gemm_h: FILM operands");
+      return launch_any<VNQA_EPI_FILM>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_PARTIAL:
+      return launch_any<VNQA_EPI_PARTIAL>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_PLAIN:
+      VNQA_REQUIRE(splits == 1, "conv_gemm_h: PLAIN cannot split K");
+      return launch_any<VNQA_EPI_PLAIN>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_DGRAD_RES:
+      VNQA_REQUIRE(!a->flat && a->add && a->res, "conv_gemm_h: DGRAD_RES operands");
+      return launch_any<VNQA_EPI_DGRAD_RES>(ncta, tmA, tmB, kp, sms, st);
+    default:
+      set_error("vnqa_conv_gemm_h: unknown epilogue %d", a->epi);
+      return -1;
+  }
+}
