@@ -1,0 +1,269 @@
+"""CANDIDATE fp16-activation orchestration of the attention model's forward / backward (not yet run on hardware).
+
+Same launch sequence as videonavqa_b200/engine.py (trunk_forward / trunk_backward / attn_forward / attn_backward); the
+differences are all about storage:
+  * trunk activations (NHWC input, BatchNorm output, every ResBlock tensor, saved z) are torch.float16 and the
+    tensor-core kernels are the kind::f16 variants of experimental/f16;
+  * BatchNorm input y0, split-K partials, FiLM parameters, the question LSTM and the attention tail stay fp32;
+  * backward signals inside the trunk are stored multiplied by LOSS_SCALE (a power of two): d feats is scaled when it
+    is converted to fp16, every kernel that leaves the fp16 domain multiplies by 1 / LOSS_SCALE.
+`install(module)` swaps these functions into ONE model instance for A/B runs; the package itself is untouched.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from videonavqa_b200 import engine as E, ops                      # noqa: E402
+from videonavqa_b200._lib import (EPI_BIAS_RELU, EPI_BIAS_RELU_AFFINE, EPI_BIAS_RELU_STATS, EPI_DGRAD_RES, EPI_FILM,  # noqa: E402
+                                  EPI_PARTIAL, EPI_PLAIN)
+import ops_f16 as H                                               # noqa: E402
+
+IMG_PIX = 130
+HALF = torch.float16
+LOSS_SCALE = float(os.environ.get("VNQA_F16_LOSS_SCALE", 4096.0))
+
+
+def _choose_splits(n_img, k_total):
+    """split-K factor for fc_embed_attn: smallest divisor of 130 that fills the SMs (K per split multiple of 64)."""
+    n_tiles = (n_img + 207) // 208
+    for s in (1, 2, 5, 10, 13, 26, 65, 130):
+        if (k_total // s) % 64 == 0 and n_tiles * s >= 140:
+            return s
+    return 130
+
+
+def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save,
+                  gen_fwd=E.lstm_generator_forward):
+    dev = v_input.device
+    c_in = v_input.shape[1]
+    C = P["conv_init.weight"].shape[0]
+    nb = 0
+    while f"film_pipeline.{nb}.weight" in P:
+        nb += 1
+    n_img = plan.n_img
+    ctx = {"plan": plan, "C": C, "nb": nb, "c_in": c_in}
+
+    x0 = H.frames_to_nhwc(v_input, plan.img_of, n_img)                      # fp16
+
+    main = torch.cuda.current_stream()
+    side = E._side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        film, gctx = gen_fwd(P, cache, plan, q_input, q_lens32, film_h, film_c, save, nb, C)
+        film.record_stream(main)
+        for t in gctx.values():
+            if torch.is_tensor(t):
+                t.record_stream(main)
+    film_ready = torch.cuda.Event()
+    film_ready.record(side)
+
+    w_init = cache.get("h.conv_init", P["conv_init.weight"], H.pack_conv_weight)
+    if training:
+        y0 = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=torch.float32)
+        stat = torch.zeros(2, plan.n_frames, C, device=dev, dtype=torch.float64)
+        H.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_STATS, out=y0,
+                    bias=P["conv_init.bias"], img_frame=plan.img_frame, stat_sum=stat[0], stat_sq=stat[1])
+        scale, shift, mean, rstd = ops.bn_finalize_train(stat[0], stat[1], plan.frame_ct, plan.n_frames,
+                                                         P["bn_init.weight"], P["bn_init.bias"], bn["running_mean"],
+                                                         bn["running_var"], E.BN_MOMENTUM, E.BN_EPS)
+        bn["num_batches_tracked"] += plan.n_frames
+        x = H.bn_apply(y0, plan.img_frame, scale, shift)
+        ctx.update(y0=y0, mean=mean, rstd=rstd)
+    else:
+        scale, shift = ops.bn_eval_affine(P["bn_init.weight"], P["bn_init.bias"], bn["running_mean"],
+                                          bn["running_var"], E.BN_EPS)
+        x = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=HALF)
+        H.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_AFFINE, out=x,
+                    bias=P["conv_init.bias"], scale=scale, shift=shift)
+
+    xs, ress, zs = [x], [], []
+    for k in range(nb):
+        w1 = cache.get(f"h.c1x1.{k}", P[f"conv1x1_layers.{k}.weight"], H.pack_conv_weight)
+        w3 = cache.get(f"h.c3x3.{k}", P[f"film_pipeline.{k}.weight"], H.pack_conv_weight)
+        res = torch.empty_like(x)
+        H.conv_gemm(w1, x, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_BIAS_RELU, out=res,
+                    bias=P[f"conv1x1_layers.{k}.bias"])
+        if k == 0:
+            main.wait_event(film_ready)
+        z = torch.empty_like(x) if save else None
+        out = torch.empty_like(x)
+        H.conv_gemm(w3, res, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_FILM, out=out,
+                    bias=P[f"film_pipeline.{k}.bias"], film=film, film_row=plan.film_row, film_ld=film.stride(0),
+                    alpha_off=2 * k * C, res=res, z_out=z)
+        x = out
+        if save:
+            xs.append(x); ress.append(res); zs.append(z)
+    if nb == 0:
+        main.wait_event(film_ready)
+    if save:
+        ctx.update(x0=x0, xs=xs, ress=ress, zs=zs, film=film)
+        ctx.update(gctx)
+    return x, ctx
+
+
+def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=E.lstm_generator_backward, mask_relu=True):
+    """dx_last: fp16, multiplied by LOSS_SCALE."""
+    plan, C, nb, c_in = ctx["plan"], ctx["C"], ctx["nb"], ctx["c_in"]
+    n_img = plan.n_img
+    dev = dx_last.device
+    un = 1.0 / LOSS_SCALE
+    film = ctx["film"]
+    dfilm = torch.zeros_like(film)
+    dout = dx_last
+    main = torch.cuda.current_stream()
+    side = E._side_stream(dev)
+    gen_done = None
+
+    def generator_backward():
+        nonlocal gen_done
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            local = E.GradSink(None)
+            gen_bwd(P, cache, ctx, dfilm, q_input, q_lens32, local)
+            for t in local.values():
+                t.record_stream(main)
+            dfilm.record_stream(side)
+            gen_done = (torch.cuda.Event(), local)
+            gen_done[0].record(side)
+
+    if nb == 0:
+        generator_backward()
+    for k in reversed(range(nb)):
+        res, z, x_in = ctx["ress"][k], ctx["zs"][k], ctx["xs"][k]
+        db3 = torch.zeros(C, device=dev, dtype=torch.float32)
+        dz = H.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3, mask_relu=mask_relu, grad_unscale=un)
+        if k == 0:
+            generator_backward()
+        grads[f"film_pipeline.{k}.bias"] = db3
+        dw3 = torch.zeros_like(P[f"film_pipeline.{k}.weight"])
+        H.conv_wgrad(dz, res, dw3, n_img=n_img, cout=C, cin=C, taps=9, grad_unscale=un)
+        grads[f"film_pipeline.{k}.weight"] = dw3
+        w3t = cache.get(f"h.c3x3t.{k}", P[f"film_pipeline.{k}.weight"], lambda w: H.pack_conv_weight(w, True))
+        db1 = torch.zeros(C, device=dev, dtype=torch.float32)
+        dpre = torch.empty_like(res)
+        H.conv_gemm(w3t, dz, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_DGRAD_RES, out=dpre, add=dout, res=res,
+                    dbias=db1, grad_unscale=un)
+        del dz
+        grads[f"conv1x1_layers.{k}.bias"] = db1
+        dw1 = torch.zeros_like(P[f"conv1x1_layers.{k}.weight"])
+        H.conv_wgrad(dpre, x_in, dw1, n_img=n_img, cout=C, cin=C, taps=1, grad_unscale=un)
+        grads[f"conv1x1_layers.{k}.weight"] = dw1
+        w1t = cache.get(f"h.c1x1t.{k}", P[f"conv1x1_layers.{k}.weight"], lambda w: H.pack_conv_weight(w, True))
+        dx = torch.empty_like(res)
+        H.conv_gemm(w1t, dpre, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_PLAIN, out=dx)
+        del dpre
+        dout = dx
+    db0 = torch.zeros(C, device=dev, dtype=torch.float32)
+    dgamma = torch.zeros(C, device=dev, dtype=torch.float32)
+    dbeta = torch.zeros(C, device=dev, dtype=torch.float32)
+    dy0 = H.bn_backward(dout, ctx["y0"], plan.img_frame, plan.frame_ct, plan.n_frames, ctx["mean"], ctx["rstd"],
+                        P["bn_init.weight"], db0, dgamma, dbeta, grad_unscale=un)
+    grads["conv_init.bias"] = db0
+    grads["bn_init.weight"] = dgamma
+    grads["bn_init.bias"] = dbeta
+    dw0 = torch.zeros_like(P["conv_init.weight"])
+    H.conv_wgrad(dy0, ctx["x0"], dw0, n_img=n_img, cout=C, cin=c_in, taps=9, grad_unscale=un)
+    grads["conv_init.weight"] = dw0
+    main.wait_event(gen_done[0])
+    for n_, t_ in gen_done[1].items():
+        grads[n_] = t_
+
+
+def attn_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, T, training, save):
+    dev = v_input.device
+    B = v_input.shape[0]
+    plan = E.Plan(v_lens_host, B, T, dev)
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
+    C, n_img = ctx["C"], plan.n_img
+    A = P["fc_attn_1.weight"].shape[1]
+    wfc = cache.get("h.fc_embed", P["fc_embed_attn.weight"], lambda w: H.to_half(ops.permute_fc_weight(w, C)))
+    K = IMG_PIX * C
+    splits = _choose_splits(n_img, K)
+    partial = torch.empty(splits, n_img, A, device=dev, dtype=torch.float32)
+    H.conv_gemm(wfc, x.view(n_img, K), taps=1, cin=K // splits, cout=A, n_img=n_img, epi=EPI_PARTIAL, out=partial,
+                flat=True, x_ld=K, splits=splits)
+    feats = torch.zeros(B, T, A, device=dev, dtype=torch.float32)
+    ops.splitk_reduce(partial, splits, n_img, A, P["fc_embed_attn.bias"], plan.feat_row, feats)
+    wih_t = cache.get("tail_wih_t", P["lstm_attn.weight_ih"], lambda w: w.t().contiguous())
+    whh_t = cache.get("tail_whh_t", P["lstm_attn.weight_hh"], lambda w: w.t().contiguous())
+    hs, coefs, cx, gates, cs = ops.attn_tail_forward(
+        feats, plan.v_lens32, plan.n_frames, P["fc_attn_1.weight"], P["fc_attn_1.bias"], P["fc_hidden_attn.weight"],
+        P["fc_hidden_attn.bias"], wih_t, whh_t, P["lstm_attn.bias_ih"], P["lstm_attn.bias_hh"], save=save)
+    logits = ops.linear(hs.view(B, T * A), P["out_linear.weight"], P["out_linear.bias"])
+    if save:
+        ctx.update(feats=feats, hs=hs, coefs=coefs, cx=cx, gates=gates, cs=cs, A=A, T=T, x_last=x)
+    return logits, ctx
+
+
+def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+    plan, C, A, T = ctx["plan"], ctx["C"], ctx["A"], ctx["T"]
+    B, n_img = plan.B, plan.n_img
+    dev = dlogits.device
+    grads = E.GradSink(grad_hook)
+    hs = ctx["hs"]
+    hs2 = hs.view(B, T * A)
+    dlogits = dlogits.contiguous()
+    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, hs2)
+    grads["out_linear.bias"] = ops.colsum(dlogits)
+    dhs = ops.linear_dgrad(dlogits, P["out_linear.weight"]).view(B, T, A)
+    dw1 = torch.zeros_like(P["fc_attn_1.weight"]); db1 = torch.zeros_like(P["fc_attn_1.bias"])
+    dwh = torch.zeros_like(P["fc_hidden_attn.weight"]); dbh = torch.zeros_like(P["fc_hidden_attn.bias"])
+    dfeats, dgates = ops.attn_tail_backward(ctx["feats"], plan.v_lens32, plan.n_frames, P["fc_attn_1.weight"],
+                                            P["fc_hidden_attn.weight"], P["lstm_attn.weight_ih"],
+                                            P["lstm_attn.weight_hh"], hs, ctx["coefs"], ctx["gates"], ctx["cs"], dhs,
+                                            dw1, db1, dwh, dbh)
+    for n_, t_ in (("fc_attn_1.weight", dw1), ("fc_attn_1.bias", db1), ("fc_hidden_attn.weight", dwh),
+                   ("fc_hidden_attn.bias", dbh)):
+        grads[n_] = t_
+    dg2 = dgates.view(B * T, 4 * A)
+    grads["lstm_attn.weight_ih"] = ops.linear_wgrad(dg2, ctx["cx"].view(B * T, A))
+    hprev = torch.zeros_like(hs)
+    hprev[:, 1:].copy_(hs[:, :-1])
+    grads["lstm_attn.weight_hh"] = ops.linear_wgrad(dg2, hprev.view(B * T, A))
+    bsum = ops.colsum(dg2)
+    grads["lstm_attn.bias_ih"] = bsum
+    grads["lstm_attn.bias_hh"] = bsum.clone()
+    # fc_embed_attn backward on the valid (clip, frame) rows; d feats enters the fp16 domain scaled
+    df_rows = ops.gather_rows(dfeats.view(B * T, A), plan.feat_row, n_img, A, round_tf32=False)
+    grads["fc_embed_attn.bias"] = ops.colsum(df_rows)
+    df_h = H.to_half(df_rows, LOSS_SCALE)
+    K = IMG_PIX * C
+    x_last = ctx["x_last"].view(n_img, K)
+    dwp = torch.zeros(A, K, device=dev, dtype=torch.float32)
+    H.conv_wgrad(df_h, x_last, dwp, n_img=n_img, cout=A, cin=K, taps=1, flat=True, grad_unscale=1.0 / LOSS_SCALE)
+    grads["fc_embed_attn.weight"] = ops.permute_fc_weight(dwp, C, inverse=True)
+    wfc_t = cache.get("h.fc_embed_t", P["fc_embed_attn.weight"],
+                      lambda w: H.pack_matrix(ops.permute_fc_weight(w, C, n_pad=w.shape[0]), transpose=True))
+    dx_last = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=HALF)
+    H.conv_gemm(wfc_t, df_h, taps=1, cin=A, cout=K, n_img=n_img, epi=EPI_PLAIN, out=dx_last, flat=True, x_ld=A)
+    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
+    return grads
+
+
+def install(module):
+    """Route ONE FiLMAttnPretrainedStem instance through the fp16 candidate path (A/B experiments only)."""
+    import types
+
+    def _forward_impl(self, P, v_input, q_input, v_lens, q_lens, save):
+        v_host, q_lens32, perm, h, c, q_in = self._prepare(v_input, q_input, v_lens, q_lens)
+        logits, ctx = attn_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, q_lens32, h, c,
+                                   self.max_num_frames, self.training, save)
+        self._finish(perm, h, c)
+        ctx["q_in"], ctx["q_lens32"] = q_in, q_lens32
+        return logits, ctx
+
+    def _backward_impl(self, P, ctx, dlogits):
+        return attn_backward(P, self._cache, ctx, dlogits, ctx["q_in"], ctx["q_lens32"],
+                             grad_hook=getattr(self, "_grad_hook", None))
+
+    module._forward_impl = types.MethodType(_forward_impl, module)
+    module._backward_impl = types.MethodType(_backward_impl, module)
+    return module

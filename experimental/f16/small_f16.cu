@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) frames_to_nhwc_h_kernel(const float* __re
   const int cs = blockIdx.y;  // channel slab
   const int b = blockIdx.z;
   const float* src = v + (((long long)b * C + cs * 64) * VNQA_IMG_PIX + p) * T;
-  for (int i = threadIdx.x; i < 64 * T; i += blockDim.x) {
+  const int nc = min(64, C - cs * 64);   // last slab may hold 32 channels
+  for (int i = threadIdx.x; i < nc * T; i += blockDim.x) {
     const int c = i / T, t = i - c * T;
     tile[c][t] = __ldg(src + (long long)c * VNQA_IMG_PIX * T + t);
   }
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) frames_to_nhwc_h_kernel(const float* __re
   const int lane = threadIdx.x & 31;
   for (int t = threadIdx.x >> 5; t < T; t += blockDim.x >> 5) {
     const int img = __ldg(img_of + b * T + t);
-    if (img >= 0)
+    if (img >= 0 && 2 * lane < nc)
       *reinterpret_cast<__half2*>(x + ((long long)img * VNQA_IMG_PIX + p) * C + cs * 64 + 2 * lane) =
           __floats2half2_rn(tile[2 * lane][t], tile[2 * lane + 1][t]);
   }
@@ -215,9 +216,9 @@ using namespace vnqa::f16;
 extern "C" int vnqa_frames_to_nhwc_h(const float* v_input, void* x_out, const int32_t* img_of, int32_t B, int32_t C,
                                      int32_t T, void* stream) {
   VNQA_REQUIRE(v_input && x_out && img_of, "vnqa_frames_to_nhwc_h: null pointer");
-  VNQA_REQUIRE(C % 64 == 0 && C > 0, "vnqa_frames_to_nhwc_h: C must be a multiple of 64 (got %d)", C);
+  VNQA_REQUIRE(C % 32 == 0 && C > 0, "vnqa_frames_to_nhwc_h: C must be a multiple of 32 (got %d)", C);
   VNQA_REQUIRE(T > 0 && T <= 64 && B > 0 && B <= 65535, "vnqa_frames_to_nhwc_h: bad B/T (%d, %d)", B, T);
-  dim3 grid(VNQA_IMG_PIX, C / 64, B);
+  dim3 grid(VNQA_IMG_PIX, (C + 63) / 64, B);
   frames_to_nhwc_h_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_input, reinterpret_cast<__half*>(x_out), img_of, C, T);
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;

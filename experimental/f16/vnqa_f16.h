@@ -58,7 +58,7 @@ int vnqa_conv_wgrad_h(const void* dy, const void* x, float* dw, float* ws, int32
                       int32_t taps, int32_t flat, float grad_unscale, void* stream);
 
 /* ---- HBM-bound kernels with fp16 trunk activations (same meaning as their fp32 namesakes in vnqa_b200.h) ---- */
-/* K0: (B, C, 10, 13, T) fp32 -> fp16 [n_img][130][C]; C multiple of 64 */
+/* K0: (B, C, 10, 13, T) fp32 -> fp16 [n_img][130][C]; C multiple of 32 */
 int vnqa_frames_to_nhwc_h(const float* v_input, void* x_out, const int32_t* img_of, int32_t B, int32_t C, int32_t T,
                           void* stream);
 /* x = fp16(y * scale[frame] + shift[frame]); y fp32 (BatchNorm input stays fp32) */
