@@ -2,7 +2,7 @@
 
     make -C experimental/f16 && python experimental/f16/check_model_f16.py [--full] [--bench]
 
-1. golden cases attn_small / attn_h128: logits vs the committed reference outputs (<= 1e-3), gradients vs the oracle
+1. the four golden cases: logits vs the committed reference outputs (<= 1e-3), gradients vs the oracle
    with fp16 operand rounding emulated (oracle = checker only);
 2. --full: eval.sh-size logits (C = 1024, 5 blocks, 4 ragged clips) vs the fp32 oracle;
 3. --bench: training-step time of the fp16 path next to the shipped tf32 path, batch 64.
@@ -64,7 +64,9 @@ def golden(name):
         e = rel_l2(g, g_emu[k])
         if e > worst:
             worst, worst_k = e, k
-    ok = e_ref <= 1e-3 and e_emu <= 3e-4 and worst <= 2e-3
+    gtol = 2e-2 if kind in ("gp", "tmh") else 2e-3      # max-pool argmax ties re-route whole gradient elements
+    ltol = 2e-3 if name == "tmh_small" else 1e-3        # same allowance as tests/test_gpu_modules.py
+    ok = e_ref <= ltol and e_emu <= 3e-4 and worst <= gtol
     print(f"{name}: logits vs reference {e_ref:.3e} (<= 1e-3), vs fp16-emulating oracle {e_emu:.3e} (<= 3e-4), "
           f"worst gradient rel-L2 vs emulating oracle {worst:.3e} [{worst_k}] (<= 2e-3)  {'ok' if ok else 'FAIL'}")
     return ok
@@ -132,7 +134,7 @@ if __name__ == "__main__":
     ap.add_argument("--bench", action="store_true")
     a = ap.parse_args()
     t0 = time.time()
-    ok = all([golden("attn_small"), golden("attn_h128")])
+    ok = all([golden(n) for n in ("attn_small", "attn_h128", "gp_small", "tmh_small")])
     if a.full:
         ok = full() and ok
     if a.bench:

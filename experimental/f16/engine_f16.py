@@ -1,4 +1,4 @@
-"""CANDIDATE fp16-activation orchestration of the attention model's forward / backward (not yet run on hardware).
+"""CANDIDATE fp16-activation orchestration of the three models' forward / backward (not yet run on hardware).
 
 Same launch sequence as videonavqa_b200/engine.py (trunk_forward / trunk_backward / attn_forward / attn_backward); the
 differences are all about storage:
@@ -248,21 +248,100 @@ def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
     return grads
 
 
+# ======================================================================================== global-pooling / multi-hop
+def _gp_tail_forward(P, cache, plan, x, ctx, B, T, save):
+    """relu(c1x1_tail) -> max over frames -> Linear; the tail map leaves the fp16 domain (out_f32)."""
+    dev = x.device
+    C, n_img = ctx["C"], plan.n_img
+    tail = P["c1x1_tail.weight"].shape[0]
+    wt = cache.get("h.c1x1_tail", P["c1x1_tail.weight"], H.pack_conv_weight)
+    y = torch.empty(n_img, IMG_PIX, tail, device=dev, dtype=torch.float32)
+    H.conv_gemm(wt, x, taps=1, cin=C, cout=tail, n_img=n_img, epi=EPI_BIAS_RELU, out=y, bias=P["c1x1_tail.bias"],
+                out_f32=True)
+    pooled, arg = ops.gp_maxpool(y, plan.img_of, B, T, tail)
+    logits = ops.linear(pooled, P["out_linear.weight"], P["out_linear.bias"])
+    if save:
+        ctx.update(pooled=pooled, arg=arg, tail=tail, x_last=x)
+    return logits, ctx
+
+
+def _gp_tail_backward(P, cache, ctx, dlogits, grads):
+    plan, C, tail = ctx["plan"], ctx["C"], ctx["tail"]
+    B, n_img = plan.B, plan.n_img
+    dev = dlogits.device
+    dlogits = dlogits.contiguous()
+    pooled = ctx["pooled"]
+    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, pooled)
+    grads["out_linear.bias"] = ops.colsum(dlogits)
+    dpooled = ops.linear_dgrad(dlogits, P["out_linear.weight"])
+    dy = ops.gp_maxpool_backward(dpooled, pooled, ctx["arg"], B, tail, n_img)     # through max + ReLU, fp32
+    grads["c1x1_tail.bias"] = ops.colsum(dy.view(n_img * IMG_PIX, tail))
+    dy_h = H.to_half(dy, LOSS_SCALE)                                               # enters the fp16 domain scaled
+    dwt = torch.zeros(tail, C, device=dev, dtype=torch.float32)
+    H.conv_wgrad(dy_h, ctx["x_last"], dwt, n_img=n_img, cout=tail, cin=C, taps=1, grad_unscale=1.0 / LOSS_SCALE)
+    grads["c1x1_tail.weight"] = dwt.view(tail, C, 1, 1)
+    wtt = cache.get("h.c1x1_tail_t", P["c1x1_tail.weight"], lambda w: H.pack_conv_weight(w, True))
+    dx_last = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=HALF)
+    H.conv_gemm(wtt, dy_h, taps=1, cin=tail, cout=C, n_img=n_img, epi=EPI_PLAIN, out=dx_last)
+    return dx_last
+
+
+def gp_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, training, save):
+    dev = v_input.device
+    B, T = v_input.shape[0], v_input.shape[-1]
+    plan = E.Plan(v_lens_host, B, T, dev)
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
+    return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
+
+
+def gp_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+    grads = E.GradSink(grad_hook)
+    dx_last = _gp_tail_backward(P, cache, ctx, dlogits, grads)
+    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
+    return grads
+
+
+def tmh_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens_host, q_lens32, film_h, film_c, training, save):
+    dev = v_input.device
+    B, T = v_input.shape[0], v_input.shape[-1]
+    plan = E.Plan(v_lens_host, B, T, dev)
+    plan.max_q_len = int(max(q_lens_host))
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save,
+                           gen_fwd=E.tmh_generator_forward)
+    return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
+
+
+def tmh_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+    grads = E.GradSink(grad_hook)
+    dx_last = _gp_tail_backward(P, cache, ctx, dlogits, grads)
+    trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=E.tmh_generator_backward, mask_relu=False)
+    return grads
+
+
 def install(module):
-    """Route ONE FiLMAttnPretrainedStem instance through the fp16 candidate path (A/B experiments only)."""
+    """Route ONE drop-in module instance (attn / gp / tmh) through the fp16 candidate path (A/B experiments only)."""
     import types
+    kind = module.kind
 
     def _forward_impl(self, P, v_input, q_input, v_lens, q_lens, save):
         v_host, q_lens32, perm, h, c, q_in = self._prepare(v_input, q_input, v_lens, q_lens)
-        logits, ctx = attn_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, q_lens32, h, c,
-                                   self.max_num_frames, self.training, save)
+        if kind == "attn":
+            logits, ctx = attn_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, q_lens32, h, c,
+                                       self.max_num_frames, self.training, save)
+        elif kind == "gp":
+            logits, ctx = gp_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, q_lens32, h, c,
+                                     self.training, save)
+        else:
+            logits, ctx = tmh_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, self._last_q_host,
+                                      q_lens32, h, c, self.training, save)
         self._finish(perm, h, c)
         ctx["q_in"], ctx["q_lens32"] = q_in, q_lens32
         return logits, ctx
 
     def _backward_impl(self, P, ctx, dlogits):
-        return attn_backward(P, self._cache, ctx, dlogits, ctx["q_in"], ctx["q_lens32"],
-                             grad_hook=getattr(self, "_grad_hook", None))
+        bwd = {"attn": attn_backward, "gp": gp_backward, "tmh": tmh_backward}[kind]
+        return bwd(P, self._cache, ctx, dlogits, ctx["q_in"], ctx["q_lens32"],
+                   grad_hook=getattr(self, "_grad_hook", None))
 
     module._forward_impl = types.MethodType(_forward_impl, module)
     module._backward_impl = types.MethodType(_backward_impl, module)
