@@ -27,20 +27,6 @@ from videonavqa_b200.models import FiLMAttnPretrainedStem    # noqa: E402
 from videonavqa_b200.synth import synthetic_batch            # noqa: E402
 
 
-class emulate_fp16:
-    """oracle.emulate_tf32() with the rounding function replaced by fp16 round-to-nearest-even."""
-
-    def __enter__(self):
-        self._old = O.tf32_round
-        O.tf32_round = lambda t: t.detach().half().float()
-        self._ctx = O.emulate_tf32()
-        self._ctx.__enter__()
-
-    def __exit__(self, *a):
-        self._ctx.__exit__(*a)
-        O.tf32_round = self._old
-
-
 def golden(name):
     kind, kw, params, grads_ref, b, z = load_case(name)
     m = engine_f16.install(build_module(kind, kw, params).train())
@@ -50,7 +36,7 @@ def golden(name):
     loss.backward()
     e_ref = norm_max_err(lo.detach().cpu(), torch.from_numpy(z["logits_train"]))
     C = kw["num_res_block_channels"]
-    with emulate_fp16():
+    with O.emulate_fp16():
         lo_emu, _, g_emu, _ = O.loss_and_grads(kind, params, O.new_bn_state(C),
                                                O.new_film_state(kw["batch_size"], kw["hidden_size"]), b["v"], b["q"],
                                                b["v_lens"], b["q_lens"], b["labels"], training=True)

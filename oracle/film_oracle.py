@@ -51,10 +51,32 @@ def tf32_round(t):
     return r
 
 
+def fp16_round(t):
+    """cvt.rn.f16.f32 and back: the same 10-bit mantissa as tf32 (round to nearest even), fp16 exponent range."""
+    return t.detach().half().float()
+
+
+_ROUND = tf32_round
+
+
+class emulate_fp16(emulate_tf32):
+    """Same rounding points as emulate_tf32(), fp16 storage (the kind::f16 candidate path, experimental/f16)."""
+
+    def __enter__(self):
+        global _ROUND
+        super().__enter__()
+        self._old_round, _ROUND = _ROUND, fp16_round
+
+    def __exit__(self, *a):
+        global _ROUND
+        _ROUND = self._old_round
+        super().__exit__(*a)
+
+
 def _q(t):
     if not _EMULATE_TF32 or t.dtype != torch.float32:
         return t
-    return t + (tf32_round(t) - t).detach()
+    return t + (_ROUND(t) - t).detach()
 
 
 # --------------------------------------------------------------------------------------

@@ -75,3 +75,24 @@ def test_q3_state_carried_across_frames():
     f0, st1 = O.film_values_lstm(params, "film_layer.", b["q"], b["q_lens"], st0)
     f1, _ = O.film_values_lstm(params, "film_layer.", b["q"], b["q_lens"], st1)
     assert float((f0 - f1).abs().max()) > 1e-6
+
+
+@pytest.mark.parametrize("name", ["attn_small", "gp_small"])
+def test_operand_rounding_emulation_stays_near_the_reference(name):
+    """emulate_tf32 / emulate_fp16 (the checker modes used by the GPU gradient tests) only perturb the fp32 result at
+    the 10-bit-mantissa level, and they are distinct roundings."""
+    kind, kw, params, _, b, z = load_case(name)
+    C = kw["num_res_block_channels"]
+    outs = {}
+    for tag, ctx in (("tf32", O.emulate_tf32()), ("fp16", O.emulate_fp16())):
+        with ctx:
+            lo, _, _, _ = O.loss_and_grads(kind, params, O.new_bn_state(C),
+                                           O.new_film_state(kw["batch_size"], kw["hidden_size"]), b["v"], b["q"],
+                                           b["v_lens"], b["q_lens"], b["labels"], training=True)
+        outs[tag] = lo
+        assert norm_max_err(lo, torch.from_numpy(z["logits_train"])) <= 2e-3, tag
+    assert not torch.equal(outs["tf32"], outs["fp16"])
+    # leaving the context restores the plain fp32 oracle
+    lo, _, _, _ = O.loss_and_grads(kind, params, O.new_bn_state(C), O.new_film_state(kw["batch_size"], kw["hidden_size"]),
+                                   b["v"], b["q"], b["v_lens"], b["q_lens"], b["labels"], training=True)
+    assert norm_max_err(lo, torch.from_numpy(z["logits_train"])) <= 2e-5

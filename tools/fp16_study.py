@@ -51,10 +51,10 @@ def main():
             if mode in ("fp16", "fp16x"):
                 pass
             if mode == "fp16":
-                O.tf32_round = lambda t: t.half().float()
+                O._ROUND = lambda t: t.half().float()
             elif mode == "bf16":
-                O.tf32_round = lambda t: t.bfloat16().float()
-        orig = O.tf32_round
+                O._ROUND = lambda t: t.bfloat16().float()
+        orig = O._ROUND
         if ctx:
             ctx.__enter__()
         try:
@@ -66,12 +66,12 @@ def main():
                 ctx.__exit__(None, None, None)
         return lo.detach(), g
 
-    base_round = O.tf32_round
+    base_round = O._ROUND
     ref, gref = run("fp32")
     for mode in ("tf32", "fp16", "bf16"):
-        O.tf32_round = base_round
+        O._ROUND = base_round
         lo, g = run(mode)
-        O.tf32_round = base_round
+        O._ROUND = base_round
         err = float((lo - ref).abs().max() / ref.abs().max())
         gl2 = {k: float((g[k] - gref[k]).norm() / gref[k].norm().clamp_min(1e-30))
                for k in ("conv_init.weight", "film_pipeline.0.weight", "film_pipeline.4.weight", "out_linear.weight")
@@ -82,9 +82,9 @@ def main():
     # backward signal range: fraction of non-zero dy elements that are sub-normal / flushed in fp16 for a loss scale
     for k in (0, 8, 12):
         del stats[:]
-        O.tf32_round = lambda t: t.half().float()
+        O._ROUND = lambda t: t.half().float()
         lo, g = run("fp16x", grad_scale=float(2 ** k))
-        O.tf32_round = base_round
+        O._ROUND = base_round
         gl2 = {n: float((g[n] - gref[n]).norm() / gref[n].norm().clamp_min(1e-30))
                for n in ("conv_init.weight", "film_pipeline.0.weight", "film_pipeline.4.weight")}
         mx = max(s_[1] for s_ in stats)
