@@ -1,6 +1,6 @@
 """Argmax-agreement report (north-star gate: >= 99.9 % over >= 4096 synthetic clips) - run on the B200 box:
 
-    python tools/argmax_agreement.py [--clips 4096] [--batch 64] [--blocks 5] [--channels 1024]
+    python tests/tools/argmax_agreement.py [--clips 4096] [--batch 64] [--blocks 5] [--channels 1024]
 
 The checker is the CPU oracle's functional code (oracle/film_oracle.py) executed on CUDA tensors in strict fp32
 (TF32 disabled in cuDNN/cuBLAS) - test infrastructure only; the product path under test is
@@ -11,7 +11,7 @@ import argparse
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

@@ -1,6 +1,6 @@
 """GPU A/B check of the fp16 candidate path (run on a B200 box; NOT part of the test suite yet).
 
-    make -C experimental/f16 && python experimental/f16/check_model_f16.py [--full] [--bench]
+    make -C experimental/f16 && python tests/tools/check_model_f16.py [--full] [--bench]
 
 1. the four golden cases: logits vs the committed reference outputs (<= 1e-3), gradients vs the oracle
    with fp16 operand rounding emulated (oracle = checker only);
@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "experimental", "f16"))
 
 import engine_f16                                            # noqa: E402
 from oracle import film_oracle as O                          # noqa: E402  (checker)

@@ -2,7 +2,7 @@
 half the HBM bytes) keep the logits inside the 1e-3 tolerance, and how small do the backward signals get?
 
 Uses the oracle's straight-through rounding hooks with the rounding function swapped (test/tool code, not product).
-    python tools/fp16_study.py [--clips 2] [--frames 4]
+    python tests/tools/fp16_study.py [--clips 2] [--frames 4]
 """
 import argparse
 import os
@@ -10,7 +10,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import film_oracle as O  # noqa: E402
 
 
