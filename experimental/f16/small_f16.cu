@@ -2,6 +2,8 @@
 // fp16 variants of K0 (layout.cu) and of bn_apply / bn_backward / film_backward (small.cu); everything else of the
 // hot path (question LSTM, attention tail, split-K reduction, BatchNorm statistics) keeps fp32 tensors and is reused.
 // All of them are pure streaming kernels: 16-byte accesses, whole pixel rows per block, fp32 arithmetic.
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 
 #include "f16_common.cuh"
@@ -49,6 +51,39 @@ __global__ void __launch_bounds__(256) frames_to_nhwc_h_kernel(const float* __re
     if (img >= 0 && 2 * lane < nc)
       *reinterpret_cast<__half2*>(x + ((long long)img * VNQA_IMG_PIX + p) * C + cs * 64 + 2 * lane) =
           __floats2half2_rn(tile[2 * lane][t], tile[2 * lane + 1][t]);
+  }
+}
+
+// K0, row-tiled (default): one block per (image row h, 64-channel slab, clip).  For one channel the 13 pixels x T frames
+// of an image row are ONE contiguous run of 13*T floats (1820 B at T = 35) in v_input, so the block reads 64 long runs
+// instead of 64 x 13 runs of 140 B, converts to fp16 into a [64][13*T] shared tile (odd pitch in 32-bit words ->
+// conflict-free column reads) and writes 13*T runs of 64 channels (128 B per warp store).
+__global__ void __launch_bounds__(256) frames_to_nhwc_h_rows_kernel(const float* __restrict__ v, __half* __restrict__ x,
+                                                                    const int* __restrict__ img_of, int C, int T,
+                                                                    int pitch) {
+  extern __shared__ __half k0_tile[];
+  const int h = blockIdx.x;   // image row 0..9
+  const int cs = blockIdx.y;  // channel slab
+  const int b = blockIdx.z;
+  const int run = VNQA_IMG_W * T;
+  const int nc = min(64, C - cs * 64);
+  const float* src = v + (((long long)b * C + cs * 64) * VNQA_IMG_PIX + h * VNQA_IMG_W) * T;
+  for (int i = threadIdx.x; i < nc * run; i += blockDim.x) {
+    const int c = i / run, j = i - c * run;
+    k0_tile[c * pitch + j] = __float2half_rn(__ldg(src + (long long)c * VNQA_IMG_PIX * T + j));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  if (2 * lane >= nc) return;
+  for (int idx = threadIdx.x >> 5; idx < run; idx += blockDim.x >> 5) {
+    const int px = idx / T, t = idx - px * T;
+    const int img = __ldg(img_of + b * T + t);
+    if (img >= 0) {
+      __half2 o;
+      o.x = k0_tile[(2 * lane) * pitch + idx];
+      o.y = k0_tile[(2 * lane + 1) * pitch + idx];
+      *reinterpret_cast<__half2*>(x + ((long long)img * VNQA_IMG_PIX + h * VNQA_IMG_W + px) * C + cs * 64 + 2 * lane) = o;
+    }
   }
 }
 
@@ -218,8 +253,19 @@ extern "C" int vnqa_frames_to_nhwc_h(const float* v_input, void* x_out, const in
   VNQA_REQUIRE(v_input && x_out && img_of, "vnqa_frames_to_nhwc_h: null pointer");
   VNQA_REQUIRE(C % 32 == 0 && C > 0, "vnqa_frames_to_nhwc_h: C must be a multiple of 32 (got %d)", C);
   VNQA_REQUIRE(T > 0 && T <= 64 && B > 0 && B <= 65535, "vnqa_frames_to_nhwc_h: bad B/T (%d, %d)", B, T);
-  dim3 grid(VNQA_IMG_PIX, (C + 63) / 64, B);
-  frames_to_nhwc_h_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_input, reinterpret_cast<__half*>(x_out), img_of, C, T);
+  const char* simple = getenv("VNQA_K0_SIMPLE");      // bring-up switch: the per-pixel kernel
+  if (simple && atoi(simple) == 1) {
+    dim3 grid(VNQA_IMG_PIX, (C + 63) / 64, B);
+    frames_to_nhwc_h_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_input, reinterpret_cast<__half*>(x_out), img_of, C, T);
+  } else {
+    // halves per channel row; odd, so lanes reading rows 2*lane (+1) at one column hit 32 different banks
+    const int pitch = (VNQA_IMG_W * T) | 1;
+    const int smem = 64 * pitch * (int)sizeof(__half);
+    VNQA_CHECK_CUDA(cudaFuncSetAttribute(frames_to_nhwc_h_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(VNQA_IMG_H, (C + 63) / 64, B);
+    frames_to_nhwc_h_rows_kernel<<<grid, 256, smem, as_stream(stream)>>>(v_input, reinterpret_cast<__half*>(x_out),
+                                                                         img_of, C, T, pitch);
+  }
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

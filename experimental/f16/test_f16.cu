@@ -407,19 +407,24 @@ static int run_small() {
     int* dio = to_dev(img_of);
     __half* dx;
     CK(cudaMalloc(&dx, (size_t)n_img * 130 * C * 2));
-    CKV(vnqa_frames_to_nhwc_h(dv, dx, dio, B, C, T, nullptr));
-    CK(cudaDeviceSynchronize());
-    auto hx = from_dev<__half>(dx, (size_t)n_img * 130 * C);
-    int bad = 0;
-    for (int b = 0; b < B; ++b)
-      for (int t = 0; t < lens[b]; ++t)
-        for (int c = 0; c < C; ++c)
-          for (int p = 0; p < 130; ++p) {
-            const float want = __half2float(__float2half_rn(v[(((size_t)b * C + c) * 130 + p) * T + t]));
-            if (__half2float(hx[((size_t)img_of[b * T + t] * 130 + p) * C + c]) != want) ++bad;
-          }
-    printf("%-30s %s\n", "frames_to_nhwc_h", bad ? "FAIL" : "ok");
-    fails += bad != 0;
+    for (int simple = 0; simple < 2; ++simple) {
+      if (simple) setenv("VNQA_K0_SIMPLE", "1", 1); else unsetenv("VNQA_K0_SIMPLE");
+      CK(cudaMemset(dx, 0xFF, (size_t)n_img * 130 * C * 2));
+      CKV(vnqa_frames_to_nhwc_h(dv, dx, dio, B, C, T, nullptr));
+      CK(cudaDeviceSynchronize());
+      auto hx = from_dev<__half>(dx, (size_t)n_img * 130 * C);
+      int bad = 0;
+      for (int b = 0; b < B; ++b)
+        for (int t = 0; t < lens[b]; ++t)
+          for (int c = 0; c < C; ++c)
+            for (int p = 0; p < 130; ++p) {
+              const float want = __half2float(__float2half_rn(v[(((size_t)b * C + c) * 130 + p) * T + t]));
+              if (__half2float(hx[((size_t)img_of[b * T + t] * 130 + p) * C + c]) != want) ++bad;
+            }
+      printf("%-30s %s\n", simple ? "frames_to_nhwc_h (per-pixel)" : "frames_to_nhwc_h (row-tiled)", bad ? "FAIL" : "ok");
+      fails += bad != 0;
+    }
+    unsetenv("VNQA_K0_SIMPLE");
     cudaFree(dv); cudaFree(dio); cudaFree(dx);
   }
   const int n_img = 6, C = 128, F = 3;
