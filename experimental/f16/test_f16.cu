@@ -396,7 +396,7 @@ static bool close_half(double got, double want, double scale) { return fabs(got 
 static int run_small() {
   int fails = 0;
   {  // ---- K0
-    const int B = 3, C = 128, T = 5, lens[3] = {5, 3, 2};
+    const int B = 3, C = 96, T = 5, lens[3] = {5, 3, 2};   // 96 = one full 64-channel slab + a 32-channel one
     std::vector<int> img_of(B * T, -1);
     int n_img = 0;
     for (int t = 0; t < T; ++t)
