@@ -123,6 +123,7 @@ struct ConvCase {
   int taps, cin, cout, n_img, flat, splits, epi;
   long long samples;  // 0 = check everything
   int iters;          // >0: time it
+  int out_f32 = 0;    // BIAS_RELU / PLAIN: fp32 output
 };
 
 static int run_conv(const ConvCase& c) {
@@ -131,7 +132,7 @@ static int run_conv(const ConvCase& c) {
   const int K = c.flat ? c.cin * c.splits : c.cin;
   const int T = 4;  // frames for STATS
   const int film_ld = 2 * c.cout + 16;
-  const bool f32out = c.epi == VNQA_EPI_BIAS_RELU_STATS || c.epi == VNQA_EPI_PARTIAL;
+  const bool f32out = c.epi == VNQA_EPI_BIAS_RELU_STATS || c.epi == VNQA_EPI_PARTIAL || c.out_f32;
   const size_t out_elems = (size_t)rows * c.cout * (c.epi == VNQA_EPI_PARTIAL ? c.splits : 1);
 
   float *dw, *dbias, *dscale, *dshift, *dfilm, *ddb;
@@ -177,7 +178,7 @@ static int run_conv(const ConvCase& c) {
   a.n_img = c.n_img; a.flat = c.flat; a.x_ld = K; a.splits = c.splits; a.epi = c.epi; a.out = dout;
   a.bias = dbias; a.scale = dscale; a.shift = dshift; a.img_frame = dframe; a.stat_sum = dsum; a.stat_sq = dsq;
   a.film = dfilm; a.film_row = dfilm_row; a.film_ld = film_ld; a.alpha_off = 8; a.res = dres; a.z_out = dz;
-  a.add = dadd; a.dbias = ddb; a.grad_unscale = 0.25f;
+  a.add = dadd; a.dbias = ddb; a.grad_unscale = 0.25f; a.out_f32 = c.out_f32;
   CKV(vnqa_conv_gemm_h(&a, nullptr));
   CK(cudaDeviceSynchronize());
 
@@ -584,6 +585,8 @@ int main(int argc, char** argv) {
       {"many_tiles_persistent", 9, 64, 512, 400, 0, 1, VNQA_EPI_FILM, 20000, 0},
       {"tail_conv1x1_cout32", 1, 256, 32, 11, 0, 1, VNQA_EPI_BIAS_RELU, 0, 0},     // gp / multi-hop tails
       {"tail_dgrad_cin32", 1, 32, 256, 11, 0, 1, VNQA_EPI_PLAIN, 0, 0},            // K completed by TMA zero fill
+      {"tail_conv1x1_cout8_f32out", 1, 128, 8, 11, 0, 1, VNQA_EPI_BIAS_RELU, 0, 0, 1},
+      {"tail_dgrad_cin8", 1, 8, 128, 11, 0, 1, VNQA_EPI_PLAIN, 0, 0},
   };
   std::vector<WgradCase> wg = {
       {"wgrad1x1_small", 1, 128, 128, 8, 0, 0},
