@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--ragged", action="store_true", help="ragged v_lens (secondary config) instead of all 35")
     ap.add_argument("--cpu-clips", type=int, default=4, help="clips in the bounded CPU sample (~10 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--candidate-fp16", action="store_true",
+                    help="A/B only: route the model through experimental/f16 (kind::f16 operands); not the product path")
     return ap.parse_args()
 
 
@@ -226,6 +228,10 @@ def gpu_leg(args):
     else:
         model = TimeMultiHopFiLMPretrainedStem(num_tail_channels=M["tail"], **common)
     model = model.to(dev)
+    if args.candidate_fp16:
+        sys.path.insert(0, os.path.join(ROOT, "experimental", "f16"))
+        import engine_f16
+        engine_f16.install(model)
     reducer = None
     _log("model on device")
     if world > 1:
@@ -356,7 +362,7 @@ def gpu_leg(args):
     bf16_peak = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)"
                 if peaks else "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)")
-    tf32_peak = bf16_peak / 2.0
+    tf32_peak = bf16_peak if args.candidate_fp16 else bf16_peak / 2.0      # kind::f16 issues at the bf16 rate
     dom_tag = f"conv_gemm.9tap.epi3.k{CFG['C']}.n{CFG['C']}"            # conv3x3 + FiLM epilogue (forward)
     kernels = summarise_kernels(klass, args.steps, ms)
     roof = None
@@ -382,7 +388,9 @@ def gpu_leg(args):
         "metric": metric_name(args),
         "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32 operands, fp32 accumulate/storage", "data": "synthetic",
+        "vs_baseline": None, "dtype": ("fp16 operands/activations (experimental/f16 candidate), fp32 accumulate"
+                                        if args.candidate_fp16 else "tf32 operands, fp32 accumulate/storage"),
+        "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "global_batch": clips, "frames_per_clip": CFG["T"], "parallelism": f"dp{world}",
                    "step": "fwd+CE(sum)+bwd" + ("+allreduce(sum)" if world > 1 else "") + "+clip_grad_norm+Adam" if train
