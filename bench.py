@@ -162,7 +162,11 @@ def hbm_roofline(kernels, peaks):
         return None
 
 
+_BEAT = [lambda what="": None]      # replaced by tools.hangwatch.beat when the stall monitor is armed
+
+
 def _log(msg):
+    _BEAT[0](msg)
     if os.environ.get("BENCH_VERBOSE"):
         print(f"[bench {time.strftime('%H:%M:%S')} rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
@@ -208,6 +212,18 @@ def gpu_leg(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stall monitor (tools/hangwatch.py): a wedged rank reports where it is wedged and exits instead of waiting for
+    # the NCCL watchdog.  On by default for multi-GPU runs; BENCH_TRACE=1 also keeps one CUDA event per launch.
+    stall_s = float(os.environ.get("BENCH_HANGWATCH_S", "90" if world > 1 else "0"))
+    beat = lambda what="": None     # noqa: E731
+    if stall_s > 0:
+        from tools import hangwatch
+        hangwatch.start(stall_s)
+        beat = hangwatch.beat
+        _BEAT[0] = beat
+        if os.environ.get("BENCH_TRACE") == "1":
+            import collections
+            ops.TRACE = collections.deque(maxlen=1200)
     dev = torch.device("cuda", local)
     if world > 1:
         _log("init_process_group")
@@ -252,6 +268,7 @@ def gpu_leg(args):
     n_frames_total = int(v_lens.sum())
 
     def step(dv, dq, dvl, dql, dlab):
+        beat("step")
         model.init_hidden()                                                        # q_and_v_eval.py:119-120
         if not train:
             with torch.no_grad():
@@ -265,9 +282,11 @@ def gpu_leg(args):
         return loss
 
     def barrier():
+        beat("barrier")
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        beat("barrier done")
 
     # ---------------- device-resident timing
     dev_in = [t.to(dev) for t in host]

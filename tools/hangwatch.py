@@ -1,0 +1,89 @@
+"""Stall monitor for multi-GPU runs (diagnostic tooling, not on the product path).
+
+    import tools.hangwatch as hw;  hw.start(stall_s=25);  hw.beat("step 3")  # call beat() whenever progress is made
+
+When no beat() arrives for `stall_s` seconds the monitor thread writes a report to stderr and to
+gpurun_out/hang_rank<R>.log and ends the process with exit code 7, so that a wedged collective or kernel shows WHERE
+it is wedged instead of sitting in the NCCL watchdog for minutes:
+
+  * the Python stack of every thread (faulthandler) - a host thread blocked in a CUDA call shows the calling line;
+  * the op trace kept by videonavqa_b200.ops (ops.TRACE): one CUDA event per C-ABI launch, queried here to name the
+    first launch that has not completed on the device;
+  * `cuda-gdb -batch` attached to this process: the kernels resident on the GPU and the native stacks
+    (skipped with HANGWATCH_GDB=0).
+"""
+import faulthandler
+import os
+import subprocess
+import sys
+import threading
+import time
+
+_last = [time.time(), "start"]
+_started = False
+
+
+def beat(what=""):
+    _last[0] = time.time()
+    _last[1] = what
+
+
+def _report(stall_s, out_dir):
+    rank = os.environ.get("RANK", "0")
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, f"hang_rank{rank}.log")
+    with open(path, "w") as f:
+        def say(msg):
+            for fh in (f, sys.stderr):
+                print(msg, file=fh, flush=True)
+        say(f"=== hangwatch rank {rank} pid {os.getpid()}: no progress for {stall_s:.0f} s after '{_last[1]}' "
+            f"at {time.strftime('%H:%M:%S')}")
+        say("--- python stacks")
+        faulthandler.dump_traceback(file=f, all_threads=True)
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        try:
+            from videonavqa_b200 import ops
+            tr = list(ops.TRACE or [])
+            say(f"--- op trace: {len(tr)} launches recorded")
+            first_pending = None
+            for i, (what, ev, stream) in enumerate(tr):
+                if not ev.query():
+                    first_pending = i
+                    break
+            if first_pending is None:
+                say("every traced launch has completed on the device")
+            else:
+                lo = max(0, first_pending - 6)
+                for i in range(lo, min(len(tr), first_pending + 8)):
+                    what, ev, stream = tr[i]
+                    say(f"  [{i}] {what:28s} stream {stream:#x} {'done' if ev.query() else 'PENDING'}")
+        except Exception as e:  # noqa: BLE001
+            say(f"op trace unavailable: {e!r}")
+        if os.environ.get("HANGWATCH_GDB", "1") != "0":
+            say("--- cuda-gdb")
+            try:
+                r = subprocess.run(["cuda-gdb", "-p", str(os.getpid()), "-batch", "-ex", "info cuda kernels", "-ex",
+                                    "info threads", "-ex", "thread apply all bt 12"], capture_output=True, text=True,
+                                   timeout=90)
+                say(r.stdout[-12000:])
+                say(r.stderr[-3000:])
+            except Exception as e:  # noqa: BLE001
+                say(f"cuda-gdb failed: {e!r}")
+    time.sleep(float(os.environ.get("HANGWATCH_LINGER_S", "40")))   # let the other ranks finish their reports
+    os._exit(7)
+
+
+def start(stall_s=30.0, out_dir=None):
+    global _started
+    if _started:
+        return
+    _started = True
+    out_dir = out_dir or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    beat("hangwatch armed")
+
+    def loop():
+        while True:
+            time.sleep(1.0)
+            if time.time() - _last[0] > stall_s:
+                _report(time.time() - _last[0], out_dir)
+    threading.Thread(target=loop, daemon=True, name="hangwatch").start()

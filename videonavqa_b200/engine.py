@@ -11,6 +11,8 @@ no tensor arithmetic is done with torch ops on the hot path.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -213,6 +215,8 @@ _SIDE = {}
 
 
 def _side_stream(dev):
+    if os.environ.get("VNQA_NO_SIDE_STREAM") == "1":     # bring-up switch: everything on the caller's stream
+        return torch.cuda.current_stream()
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)

@@ -17,11 +17,17 @@ _KERNELS_PER_CALL = {"bn_backward": 3, "vnqa_device_check": 0, "conv_wgrad": 1} 
 def check(rc, what):
     _check(rc, what)
     _count(_KERNELS_PER_CALL.get(what, 1))
+    if TRACE is not None:       # diagnostics only (tools/hangwatch.py): one event per launch on the launching stream
+        st = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(st)
+        TRACE.append((what, ev, st.cuda_stream))
 
 # ---- measurement hooks (bench.py): kernel-launch counter and optional per-launch CUDA-event timing of the
 # tensor-core kernels on the stream they are launched on.  Off by default; they never change what is computed.
 LAUNCHES = 0
 PROFILE = None      # list of (tag, flops, start_event, end_event) when enabled
+TRACE = None        # collections.deque of (entry point, completion event, stream) when enabled (tools/hangwatch.py)
 
 
 def _count(n=1):
