@@ -32,6 +32,12 @@ const char* vnqa_last_error(void);
 /* 0 iff the current CUDA device is sm_100 (B200); the product path has no other backend. */
 int vnqa_device_check(void);
 int vnqa_sm_count(void);
+/* Pipeline bring-up only (libvnqa_b200_dbg.so, built with -DVNQA_DEBUG_MBAR): `host_mapped` is pinned host memory of
+ * 148*8 records x 32 uint64 in which a tensor-core kernel whose mbarrier wait exceeds 2 s records who is waiting and
+ * the raw state of the CTA's barriers (csrc/ptx.cuh).  The release library accepts the call and ignores the buffer.
+ * vnqa_debug_build() returns 1 for the debug library. */
+int vnqa_debug_install(void* host_mapped);
+int vnqa_debug_build(void);
 
 /* ---- K0: (B, C, 10, 13, T) fp32, T innermost  ->  frame-image-major NHWC [n_img][130][C].
  * Replaces the strided slice v_input[:ct, :, :, :, i] (models/film_attn_pt_stem.py:210).

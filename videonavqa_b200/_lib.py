@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvnqa_b200.so")
+# VNQA_LIB_PATH selects another build of the same library (the -DVNQA_DEBUG_MBAR bring-up build)
+LIB_PATH = os.environ.get("VNQA_LIB_PATH") or os.path.join(_HERE, "libvnqa_b200.so")
 
 
 class VnqaError(RuntimeError):
@@ -42,6 +43,8 @@ SIGNATURES = {
     "vnqa_last_error": [],
     "vnqa_device_check": [],
     "vnqa_sm_count": [],
+    "vnqa_debug_install": [P],
+    "vnqa_debug_build": [],
     "vnqa_frames_to_nhwc": [P, P, P, I32, I32, I32, P],
     "vnqa_pack_conv_weight": [P, P, I32, I32, I32, I32, I32, P],
     "vnqa_permute_fc_weight": [P, P, I32, I32, I32, I32, P],

@@ -58,7 +58,22 @@ int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* di
   return 0;
 }
 
+static unsigned long long* g_dbg = nullptr;
+unsigned long long* debug_buffer() { return g_dbg; }
+
 }  // namespace vnqa
+
+extern "C" int vnqa_debug_install(void* host_mapped) {
+  vnqa::g_dbg = static_cast<unsigned long long*>(host_mapped);
+  return 0;
+}
+extern "C" int vnqa_debug_build(void) {
+#ifdef VNQA_DEBUG_MBAR
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 extern "C" int vnqa_abi_version(void) { return VNQA_ABI_VERSION; }
 extern "C" const char* vnqa_last_error(void) { return vnqa::g_err; }

@@ -40,6 +40,9 @@ EncodeTiledFn get_encode_tiled();
 int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, bool atom32 = false);
 
+// host-mapped diagnostics buffer installed by vnqa_debug_install (nullptr unless a debug session set one)
+unsigned long long* debug_buffer();
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace vnqa

@@ -66,6 +66,7 @@ struct KParams {
   float* z_out;
   const float* add;
   float* dbias;
+  unsigned long long* dbg;   // VNQA_DEBUG_MBAR builds: host-mapped diagnostics buffer (ptx.cuh), else unused
 };
 
 __device__ __forceinline__ float rnd(float x, int no_round) { return no_round ? x : tf32_round(x); }
@@ -229,6 +230,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int first_item = blockIdx.x / NCTA;
   const int item_stride = gridDim.x / NCTA;
   const int k_iters = p.taps * p.k_chunks;
+  const DbgCtx dbg{p.dbg, full_bar, 2 * C::STAGES + 4};
+  (void)dbg;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -270,7 +273,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int dy = 0, dx = 0;
         if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          MBAR_WAIT(&empty_bar[stage], phase ^ 1, 1, ((long long)item << 20) | (tap << 12) | kc);
           if (elect_one()) {
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
@@ -306,11 +309,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     for (int item = first_item; item < total_items; item += item_stride) {
-      mbar_wait(&acc_empty[as], aphase ^ 1, 2);
+      MBAR_WAIT(&acc_empty[as], aphase ^ 1, 2, ((long long)item << 20));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * ACC_COLS;
       for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase, 3);
+        MBAR_WAIT(&full_bar[stage], phase, 3, ((long long)item << 20) | it);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -344,7 +347,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t aphase = 0;
     for (int item = first_item; item < total_items; item += item_stride) {
       const TileCoord tc = decode_tile<NCTA>(item, p, rank);
-      mbar_wait(&acc_full[as], aphase, 4);
+      MBAR_WAIT(&acc_full[as], aphase, 4, ((long long)item << 20));
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * ACC_COLS;
       epilogue_tile<EPI>(p, tc, t_base, ew, lane);
@@ -431,6 +434,7 @@ extern "C" int vnqa_conv_gemm(const vnqa_conv_args* a, void* stream) {
   kp.img_frame = a->img_frame; kp.stat_sum = a->stat_sum; kp.stat_sq = a->stat_sq;
   kp.film = a->film; kp.film_row = a->film_row; kp.film_ld = a->film_ld; kp.alpha_off = a->alpha_off;
   kp.res = a->res; kp.z_out = a->z_out; kp.add = a->add; kp.dbias = a->dbias;
+  kp.dbg = debug_buffer();
 
   // CTA pairs (cta_group::2) whenever the output channels split into an even number of 128-row tiles
   int ncta = (kp.m_tiles % 2 == 0) ? 2 : 1;

@@ -66,18 +66,65 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Blocking wait with a watchdog: a pipeline bug traps (reported as a CUDA error with the barrier tag) instead of
-// hanging the GPU.  try_wait suspends the thread for a hardware time slice, so the spin count stays small.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  uint32_t spins = 0;
+// Blocking wait.  try_wait suspends the thread for a hardware time slice, so the loop is not a hot spin.  Release
+// builds wait without a bound: a legitimately long wait (SM time-slicing, a co-resident collective, a profiler or
+// sanitizer replay) must not abort training.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 21)) {
-      printf("vnqa: mbarrier wait timed out (block %d thread %d tag %d parity %u)\n", blockIdx.x, threadIdx.x, tag,
-             parity);
-      __trap();
+  }
+}
+
+// -DVNQA_DEBUG_MBAR (libvnqa_b200_dbg.so, pipeline bring-up only): a wait that lasts longer than 2 s of %globaltimer
+// writes a record into a host-mapped buffer installed with vnqa_debug_install() - who waits (block, thread, role tag,
+// loop counters) plus the raw 64-bit state of every mbarrier of the CTA - and keeps waiting, so that a host-side
+// monitor (tools/hangwatch.py) can print what a wedged kernel is waiting for without any CUDA call.
+struct DbgCtx {
+  unsigned long long* buf;   // host-mapped, VNQA_DBG_SLOTS records of VNQA_DBG_REC words; nullptr = off
+  const uint64_t* bars;      // first mbarrier of this CTA
+  int nbars;
+};
+constexpr int VNQA_DBG_REC = 32;
+constexpr int VNQA_DBG_SLOTS = 148 * 8;
+#ifdef VNQA_DEBUG_MBAR
+static __device__ __noinline__ void mbar_dbg_record(const DbgCtx& d, uint64_t* bar, uint32_t parity, int tag, long long info,
+                                             unsigned rounds) {
+  if (d.buf == nullptr) return;
+  const int slot = (blockIdx.x * 8 + (threadIdx.x >> 5)) % VNQA_DBG_SLOTS;
+  volatile unsigned long long* r = d.buf + (size_t)slot * VNQA_DBG_REC;
+  uint32_t smid, crank;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  r[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+  r[2] = ((unsigned long long)tag << 32) | (parity << 16) | (unsigned)(bar - d.bars);
+  r[3] = (unsigned long long)info;
+  r[4] = ((unsigned long long)smid << 32) | (crank << 16) | rounds;
+  for (int i = 0; i < d.nbars && i < VNQA_DBG_REC - 6; ++i) {
+    unsigned long long w;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(w) : "r"(smem_u32(d.bars + i)));
+    r[6 + i] = w;
+  }
+  __threadfence_system();
+  r[0] = 0x564E5141ull;   // "VNQA": record valid
+}
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int tag, long long info, const DbgCtx& d) {
+  uint64_t t0 = 0;
+  uint32_t spins = 0, rounds = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2000000000ull) {
+        if ((threadIdx.x & 31) == 0) mbar_dbg_record(d, bar, parity, tag, info, ++rounds);
+        t0 = now;
+      }
     }
   }
 }
+#define MBAR_WAIT(bar, parity, tag, info) mbar_wait_dbg(bar, parity, tag, (long long)(info), dbg)
+#else
+#define MBAR_WAIT(bar, parity, tag, info) mbar_wait(bar, parity)
+#endif
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

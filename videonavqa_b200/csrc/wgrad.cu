@@ -42,6 +42,7 @@ struct WParams {
   int taps, m_tiles, n_tiles, splits, n_chunks, chunks_per_split, flat;
   int cout, cin;          // real sizes (tiles beyond are skipped on store)
   float* out;             // [taps][cout][cin] accumulation buffer (== dw when taps == 1)
+  unsigned long long* dbg;   // VNQA_DEBUG_MBAR builds only
 };
 
 // m_tiles counts 128-row co tiles, n_tiles counts (128*NCTA)-wide ci tiles.
@@ -66,6 +67,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int base_items = mg * p.n_tiles * p.taps;
   const int total_items = base_items * p.splits;
   const int first_item = blockIdx.x / NCTA, item_stride = gridDim.x / NCTA;
+  const DbgCtx dbg{p.dbg, full_bar, 2 * WG_STAGES + 4};
+  (void)dbg;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -104,7 +107,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int c_end = min(c_begin + p.chunks_per_split, p.n_chunks);
       const int ci0 = nt * N_INSTR + rank * WG_NB;   // this CTA's 128 input channels of the tile
       for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        MBAR_WAIT(&empty_bar[stage], phase ^ 1, 1, ((long long)item << 20) | c);
         if (elect_one()) {
           uint8_t* sa = smem + stage * WG_STAGE_BYTES;
           uint8_t* sb = sa + WG_A_BYTES;
@@ -144,11 +147,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       decode(item, mt, nt, tap, sp);
       const int c_begin = sp * p.chunks_per_split;
       const int c_end = min(c_begin + p.chunks_per_split, p.n_chunks);
-      mbar_wait(&acc_empty[as], aphase ^ 1, 2);
+      MBAR_WAIT(&acc_empty[as], aphase ^ 1, 2, ((long long)item << 20));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * N_INSTR;
       for (int c = c_begin; c < c_end; ++c) {
-        mbar_wait(&full_bar[stage], phase, 3);
+        MBAR_WAIT(&full_bar[stage], phase, 3, ((long long)item << 20) | c);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
@@ -180,7 +183,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int item = first_item; item < total_items; item += item_stride) {
       int mt, nt, tap, sp;
       decode(item, mt, nt, tap, sp);
-      mbar_wait(&acc_full[as], aphase, 4);
+      MBAR_WAIT(&acc_full[as], aphase, 4, ((long long)item << 20));
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * N_INSTR;
       float* tile_s = scratch + ew * (32 * 33);
@@ -281,6 +284,7 @@ extern "C" int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, float
   wp.cin = cin;
   wp.n_chunks = flat ? (n_img + WG_KP - 1) / WG_KP : ((n_img + 3) / 4) * 5;
   wp.out = taps == 1 ? dw : ws;
+  wp.dbg = debug_buffer();
   const int sms = vnqa_sm_count();
   if (sms <= 0) return -2;
   // split-K: (a) one split's slice of dY and X (chunks * 104 rows * (cout+cin) * 4 B) should stay L2-resident while
