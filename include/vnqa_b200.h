@@ -207,6 +207,40 @@ int vnqa_attn_tail_backward(const float* feats, const int32_t* v_lens, int32_t n
                             const float* coefs, const float* gates, const float* cs, const float* dhs, float* dfeats,
                             float* dgates, float* dw1, float* db1, float* dwh, float* dbh, void* stream);
 
+/* ---- global-norm clip + Adam over FLAT fp32 buffers (n multiple of 4, 16-byte aligned);
+ * replaces clip_grad_norm(model.parameters(), 1.0) + optimizer.step() of eval/q_and_v_eval.py:137-139.
+ * vnqa_sumsq_partials writes vnqa_opt_num_partials() per-block sums of g^2 (fp64, no atomics -> deterministic);
+ * vnqa_clip_adam reduces them in a fixed order, scales the gradient by grad_scale * min(1, max_norm / (norm + 1e-6))
+ * (max_norm <= 0: no clipping, partials may be NULL) and applies torch.optim.Adam's update (no amsgrad, no weight
+ * decay) with the host-computed bias corrections 1 - beta1^t and sqrt(1 - beta2^t).  norm_out (optional) receives
+ * the total gradient norm that clip_grad_norm_ would return. */
+int vnqa_opt_num_partials(void);
+int vnqa_sumsq_partials(const float* g, int64_t n, double* partials, void* stream);
+int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const double* partials, int32_t n_partials,
+                   float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                   float bias_correction1, float bias_correction2_sqrt, float* norm_out, void* stream);
+
+/* ---- K10 (new - the reference is single-GPU): gradient all-reduce over NVLink / NVSwitch.
+ * One process per GPU owns one ncclComm_t and one dedicated communication stream inside the library.  NCCL is
+ * dlopen'ed (vnqa_nccl_load; NULL = "libnccl.so.2").  Rank 0 creates the 128-byte unique id, every rank calls
+ * vnqa_nccl_init with it (collective).  vnqa_nccl_allreduce_sum_f32 enqueues an IN-PLACE SUM all-reduce on the
+ * communication stream ordered after everything queued so far on `after_stream` and returns at once, so the
+ * collective overlaps the remaining backward kernels; vnqa_nccl_join makes a stream wait for all queued collectives.
+ * SUM, not mean: the reference loss is CrossEntropyLoss(reduction='sum') (eval.sh:15).  Errors return -4. */
+int vnqa_nccl_load(const char* libpath);
+int vnqa_nccl_version(void);
+int vnqa_nccl_unique_id(void* out128);
+int vnqa_nccl_init(const void* id128, int32_t rank, int32_t nranks);
+int vnqa_nccl_rank(void);
+int vnqa_nccl_nranks(void);
+void* vnqa_nccl_stream(void);
+int vnqa_nccl_allreduce_sum_f32(float* buf, int64_t count, void* after_stream);
+int vnqa_nccl_allgather_f64(const double* send, double* recv, int64_t count, void* after_stream);
+int vnqa_nccl_broadcast_f32(float* buf, int64_t count, int32_t root, void* after_stream);
+int vnqa_nccl_join(void* stream);
+int vnqa_nccl_destroy(void);
+int vnqa_nccl_abort(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,10 +70,26 @@ SIGNATURES = {
     "vnqa_tmh_hops_backward": [P, P, P, P, P, I32, I32, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "vnqa_ln_slice_forward": [P, I32, I32, P, P, P, I32, I32, I32, P, P, P],
     "vnqa_ln_slice_backward": [P, I32, I32, P, P, I32, I32, I32, P, P, P, P, P, P],
+    "vnqa_nccl_load": [c_char_p],
+    "vnqa_nccl_version": [],
+    "vnqa_nccl_unique_id": [P],
+    "vnqa_nccl_init": [P, I32, I32],
+    "vnqa_nccl_rank": [],
+    "vnqa_nccl_nranks": [],
+    "vnqa_nccl_stream": [],
+    "vnqa_nccl_allreduce_sum_f32": [P, I64, P],
+    "vnqa_nccl_allgather_f64": [P, P, I64, P],
+    "vnqa_nccl_broadcast_f32": [P, I64, I32, P],
+    "vnqa_nccl_join": [P],
+    "vnqa_nccl_destroy": [],
+    "vnqa_nccl_abort": [],
+    "vnqa_opt_num_partials": [],
+    "vnqa_sumsq_partials": [P, I64, P, P],
+    "vnqa_clip_adam": [P, P, P, P, I64, P, I32, F32, F32, F32, F32, F32, F32, F32, F32, P, P],
     "vnqa_attn_tail_forward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "vnqa_attn_tail_backward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
 }
-_RESTYPES = {"vnqa_last_error": c_char_p}
+_RESTYPES = {"vnqa_last_error": c_char_p, "vnqa_nccl_stream": c_void_p}
 
 _lib = None
 

@@ -77,6 +77,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * NCTA); }
     fence_mbar_init();
   }
+  // A CTA pair allocates tensor memory with a PAIR-wide instruction (UTCATOMSWS.2CTA): both CTAs must be resident
+  // and past their barrier initialisation before either issues it.  The CTAs of a cluster can start staggered when
+  // the cluster lands on SMs that other work has just vacated (a persistent grid sharing the GPU with another
+  // stream); an alloc issued before the peer was up wedged the peer's own alloc for good (round-2 probe,
+  // profiles/r02_dp_hang_rootcause.md).  Hence: cluster barrier, THEN alloc, then the usual fence/barrier/fence.
+  if (NCTA == 2) cluster_sync_all();
   if (warp == 2) {
     if (NCTA == 2) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
     else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -217,11 +223,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
   tc_fence_before();
-  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's smem until the end
   if (warp == 2) {
     if (NCTA == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  // neither CTA of a pair leaves (and frees its SM for the next cluster) before BOTH have released their tensor memory
+  if (NCTA == 2) cluster_sync_all();
 }
 
 // [tap][co][ci] -> (co, ci, tap)
