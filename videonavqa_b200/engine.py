@@ -70,12 +70,20 @@ class Plan:
 
 
 class GradSink(dict):
-    """name -> gradient; calls ``hook(name, tensor)`` the moment a gradient is final so that a data-parallel
-    wrapper can start its all-reduce while the rest of the backward pass is still running (videonavqa_b200.dp)."""
+    """name -> gradient.  ``buffer(name, like)`` hands out the tensor a gradient is written into: a view of the flat
+    gradient bucket when one is installed (videonavqa_b200.optim.FlatBuffers - zeroed once at the start of backward,
+    all-reduced and consumed by the optimizer in place), else a fresh zero tensor.  ``sink[name] = t`` publishes a
+    finished gradient and calls ``hook(name, t)`` so that a data-parallel reducer can start its all-reduce while the
+    rest of the backward pass is still running (videonavqa_b200.dp)."""
 
-    def __init__(self, hook=None):
+    def __init__(self, hook=None, bucket=None):
         super().__init__()
         self._hook = hook
+        self._bucket = bucket
+
+    def buffer(self, name, like):
+        v = self._bucket.get(name) if self._bucket is not None else None
+        return v if v is not None else torch.zeros_like(like)
 
     def __setitem__(self, name, tensor):
         super().__setitem__(name, tensor)
@@ -84,19 +92,31 @@ class GradSink(dict):
 
 
 class WeightCache:
-    """Kernel-friendly repacks of the PyTorch-layout parameters; derived data, rebuilt when a parameter's
-    version counter or storage changes (load_state_dict, optimizer step, .cuda())."""
+    """Kernel-friendly repacks of the PyTorch-layout parameters; derived data, rebuilt when a parameter's version
+    counter or storage changes (load_state_dict, optimizer step, .cuda()) or after ``invalidate()`` - needed when the
+    weights are written through ``.data`` or raw pointers, which do not bump the version counter (broadcasts, the
+    fused optimizer)."""
 
     def __init__(self):
         self._c = {}
+        self._gen = {}          # data_ptr -> generation, bumped by invalidate(tensors)
+        self._all = 0
 
     def get(self, key, tensor, build):
-        tag = (tensor.data_ptr(), tensor._version, tuple(tensor.shape))
+        ptr = tensor.data_ptr()
+        tag = (ptr, tensor._version, tuple(tensor.shape), self._all, self._gen.get(ptr, 0))
         hit = self._c.get(key)
         if hit is None or hit[0] != tag:
             hit = (tag, build(tensor))
             self._c[key] = hit
         return hit[1]
+
+    def invalidate(self, tensors=None):
+        if tensors is None:
+            self._all += 1
+            return
+        for t in tensors:
+            self._gen[t.data_ptr()] = self._gen.get(t.data_ptr(), 0) + 1
 
 
 def _choose_splits(n_img, k_total):
@@ -131,8 +151,8 @@ def lstm_generator_backward(P, cache, ctx, dfilm, q_input, q_lens32, sink):
     h_pass = ctx["h_pass"]
     H = h_pass.shape[-1]
     hp2 = h_pass.view(plan.n_frames * plan.B, H)
-    sink[lin + "weight"] = ops.linear_wgrad(dfilm, hp2)
-    sink[lin + "bias"] = ops.colsum(dfilm)
+    sink[lin + "weight"] = ops.linear_wgrad(dfilm, hp2, out=sink.buffer(lin + "weight", P[lin + "weight"]))
+    sink[lin + "bias"] = ops.colsum(dfilm, out=sink.buffer(lin + "bias", P[lin + "bias"]))
     dh_pass = ops.linear_dgrad(dfilm, P[lin + "weight"])
     question_backward(P, ctx, dh_pass, q_input, q_lens32, sink, enc)
 
@@ -243,7 +263,7 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
         nonlocal gen_done
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            local = GradSink(None)
+            local = GradSink(None, grads._bucket if isinstance(grads, GradSink) else None)
             gen_bwd(P, cache, ctx, dfilm, q_input, q_lens32, local)
             for t in local.values():
                 t.record_stream(main)
@@ -255,22 +275,22 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
         generator_backward()
     for k in reversed(range(nb)):
         res, z, x_in = ctx["ress"][k], ctx["zs"][k], ctx["xs"][k]
-        db3 = torch.zeros(C, device=dev, dtype=torch.float32)
+        db3 = grads.buffer(f"film_pipeline.{k}.bias", P[f"film_pipeline.{k}.bias"])
         dz = ops.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3, mask_relu=mask_relu)
         if k == 0:
             generator_backward()
         grads[f"film_pipeline.{k}.bias"] = db3
-        dw3 = torch.zeros_like(P[f"film_pipeline.{k}.weight"])
+        dw3 = grads.buffer(f"film_pipeline.{k}.weight", P[f"film_pipeline.{k}.weight"])
         ops.conv_wgrad(dz, res, dw3, n_img=n_img, cout=C, cin=C, taps=9)
         grads[f"film_pipeline.{k}.weight"] = dw3
         w3t = cache.get(f"c3x3t.{k}", P[f"film_pipeline.{k}.weight"], lambda w: ops.pack_conv_weight(w, True))
-        db1 = torch.zeros(C, device=dev, dtype=torch.float32)
+        db1 = grads.buffer(f"conv1x1_layers.{k}.bias", P[f"conv1x1_layers.{k}.bias"])
         dpre = torch.empty_like(res)
         ops.conv_gemm(w3t, dz, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_DGRAD_RES, out=dpre, add=dout, res=res,
                       dbias=db1)
         del dz
         grads[f"conv1x1_layers.{k}.bias"] = db1
-        dw1 = torch.zeros_like(P[f"conv1x1_layers.{k}.weight"])
+        dw1 = grads.buffer(f"conv1x1_layers.{k}.weight", P[f"conv1x1_layers.{k}.weight"])
         ops.conv_wgrad(dpre, x_in, dw1, n_img=n_img, cout=C, cin=C, taps=1)
         grads[f"conv1x1_layers.{k}.weight"] = dw1
         w1t = cache.get(f"c1x1t.{k}", P[f"conv1x1_layers.{k}.weight"], lambda w: ops.pack_conv_weight(w, True))
@@ -279,15 +299,15 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
         del dpre
         dout = dx
     # ---- BatchNorm + ReLU + conv_init
-    db0 = torch.zeros(C, device=dev, dtype=torch.float32)
-    dgamma = torch.zeros(C, device=dev, dtype=torch.float32)
-    dbeta = torch.zeros(C, device=dev, dtype=torch.float32)
+    db0 = grads.buffer("conv_init.bias", P["conv_init.bias"])
+    dgamma = grads.buffer("bn_init.weight", P["bn_init.weight"])
+    dbeta = grads.buffer("bn_init.bias", P["bn_init.bias"])
     dy0 = ops.bn_backward(dout, ctx["y0"], plan.img_frame, plan.frame_ct, plan.n_frames, ctx["mean"], ctx["rstd"],
                           P["bn_init.weight"], db0, dgamma, dbeta)
     grads["conv_init.bias"] = db0
     grads["bn_init.weight"] = dgamma
     grads["bn_init.bias"] = dbeta
-    dw0 = torch.zeros_like(P["conv_init.weight"])
+    dw0 = grads.buffer("conv_init.weight", P["conv_init.weight"])
     ops.conv_wgrad(dy0, ctx["x0"], dw0, n_img=n_img, cout=C, cin=c_in, taps=9)
     grads["conv_init.weight"] = dw0
     # ---- join the side stream; its gradients are published (and all-reduced, if a hook is set) from the main stream
@@ -305,16 +325,18 @@ def question_backward(P, ctx, dh_pass, q_input, q_lens32, grads, enc, dh_steps=N
     dgates, dgx = ops.lstm_chain_backward(dh_pass, q_lens32, P[enc + "weight_hh_l0"], sg, sc, ctx["c0"],
                                           dh_steps=dh_steps)
     steps = n_pass * B * L
-    grads[enc + "weight_hh_l0"] = ops.linear_wgrad(dgates.view(steps, H4), sh.view(steps, H), ksplit=64)
+    grads[enc + "weight_hh_l0"] = ops.linear_wgrad(dgates.view(steps, H4), sh.view(steps, H), ksplit=64,
+                                                   out=grads.buffer(enc + "weight_hh_l0", P[enc + "weight_hh_l0"]))
     dgx2 = dgx.view(B * L, H4)
     xemb = ops.embed_gather(q_input, q_lens32, P["embed.weight"])
     E = xemb.shape[-1]
-    grads[enc + "weight_ih_l0"] = ops.linear_wgrad(dgx2, xemb.view(B * L, E), ksplit=8)
-    bsum = ops.colsum(dgx2)
+    grads[enc + "weight_ih_l0"] = ops.linear_wgrad(dgx2, xemb.view(B * L, E), ksplit=8,
+                                                   out=grads.buffer(enc + "weight_ih_l0", P[enc + "weight_ih_l0"]))
+    bsum = ops.colsum(dgx2, out=grads.buffer(enc + "bias_ih_l0", P[enc + "bias_ih_l0"]))
     grads[enc + "bias_ih_l0"] = bsum
-    grads[enc + "bias_hh_l0"] = bsum.clone()
+    grads[enc + "bias_hh_l0"] = grads.buffer(enc + "bias_hh_l0", P[enc + "bias_hh_l0"]).copy_(bsum)
     dxemb = ops.linear_dgrad(dgx2, P[enc + "weight_ih_l0"])
-    dembed = torch.zeros_like(P["embed.weight"])
+    dembed = grads.buffer("embed.weight", P["embed.weight"])
     ops.embed_backward(q_input, q_lens32, dxemb, dembed)
     grads["embed.weight"] = dembed
 
@@ -349,19 +371,20 @@ def attn_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, 
     return logits, ctx
 
 
-def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
+def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None, grad_bucket=None):
     plan, C, A, T = ctx["plan"], ctx["C"], ctx["A"], ctx["T"]
     B, n_img = plan.B, plan.n_img
     dev = dlogits.device
-    grads = GradSink(grad_hook)
+    grads = GradSink(grad_hook, grad_bucket)
+    buf = lambda n: grads.buffer(n, P[n])     # noqa: E731
     hs = ctx["hs"]
     hs2 = hs.view(B, T * A)
     dlogits = dlogits.contiguous()
-    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, hs2)
-    grads["out_linear.bias"] = ops.colsum(dlogits)
+    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, hs2, out=buf("out_linear.weight"))
+    grads["out_linear.bias"] = ops.colsum(dlogits, out=buf("out_linear.bias"))
     dhs = ops.linear_dgrad(dlogits, P["out_linear.weight"]).view(B, T, A)
-    dw1 = torch.zeros_like(P["fc_attn_1.weight"]); db1 = torch.zeros_like(P["fc_attn_1.bias"])
-    dwh = torch.zeros_like(P["fc_hidden_attn.weight"]); dbh = torch.zeros_like(P["fc_hidden_attn.bias"])
+    dw1, db1 = buf("fc_attn_1.weight"), buf("fc_attn_1.bias")
+    dwh, dbh = buf("fc_hidden_attn.weight"), buf("fc_hidden_attn.bias")
     dfeats, dgates = ops.attn_tail_backward(ctx["feats"], plan.v_lens32, plan.n_frames, P["fc_attn_1.weight"],
                                             P["fc_hidden_attn.weight"], P["lstm_attn.weight_ih"],
                                             P["lstm_attn.weight_hh"], hs, ctx["coefs"], ctx["gates"], ctx["cs"], dhs,
@@ -370,21 +393,21 @@ def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
                    ("fc_hidden_attn.bias", dbh)):
         grads[n_] = t_
     dg2 = dgates.view(B * T, 4 * A)
-    grads["lstm_attn.weight_ih"] = ops.linear_wgrad(dg2, ctx["cx"].view(B * T, A))
+    grads["lstm_attn.weight_ih"] = ops.linear_wgrad(dg2, ctx["cx"].view(B * T, A), out=buf("lstm_attn.weight_ih"))
     hprev = torch.zeros_like(hs)
     hprev[:, 1:].copy_(hs[:, :-1])               # data movement only: h_{i-1} with h_{-1} = 0
-    grads["lstm_attn.weight_hh"] = ops.linear_wgrad(dg2, hprev.view(B * T, A))
-    bsum = ops.colsum(dg2)
+    grads["lstm_attn.weight_hh"] = ops.linear_wgrad(dg2, hprev.view(B * T, A), out=buf("lstm_attn.weight_hh"))
+    bsum = ops.colsum(dg2, out=buf("lstm_attn.bias_ih"))
     grads["lstm_attn.bias_ih"] = bsum
-    grads["lstm_attn.bias_hh"] = bsum.clone()
+    grads["lstm_attn.bias_hh"] = buf("lstm_attn.bias_hh").copy_(bsum)
     # fc_embed_attn backward on the valid (clip, frame) rows
     df_rows = ops.gather_rows(dfeats.view(B * T, A), plan.feat_row, n_img, A, round_tf32=True)
-    grads["fc_embed_attn.bias"] = ops.colsum(df_rows)
+    grads["fc_embed_attn.bias"] = ops.colsum(df_rows, out=buf("fc_embed_attn.bias"))
     K = IMG_PIX * C
     x_last = ctx["x_last"].view(n_img, K)
     dwp = torch.zeros(A, K, device=dev, dtype=torch.float32)
     ops.conv_wgrad(df_rows, x_last, dwp, n_img=n_img, cout=A, cin=K, taps=1, flat=True)
-    grads["fc_embed_attn.weight"] = ops.permute_fc_weight(dwp, C, inverse=True)
+    grads["fc_embed_attn.weight"] = ops.permute_fc_weight(dwp, C, inverse=True, out=buf("fc_embed_attn.weight"))
     wfc = cache.get("fc_embed", P["fc_embed_attn.weight"], lambda w: ops.permute_fc_weight(w, C))
     wfc_t = cache.get("fc_embed_t", P["fc_embed_attn.weight"],
                       lambda w: ops.pack_matrix(ops.permute_fc_weight(w, C, n_pad=w.shape[0]), transpose=True))
@@ -421,8 +444,8 @@ def _gp_tail_forward(P, cache, plan, x, ctx, B, T, save):
     return logits, ctx
 
 
-def gp_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
-    grads = GradSink(grad_hook)
+def gp_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None, grad_bucket=None):
+    grads = GradSink(grad_hook, grad_bucket)
     dx_last = _gp_tail_backward(P, ctx, dlogits, grads)
     trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
     return grads
@@ -433,15 +456,17 @@ def _gp_tail_backward(P, ctx, dlogits, grads):
     B, n_img = plan.B, plan.n_img
     dlogits = dlogits.contiguous()
     pooled = ctx["pooled"]
-    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, pooled)
-    grads["out_linear.bias"] = ops.colsum(dlogits)
+    grads["out_linear.weight"] = ops.linear_wgrad(dlogits, pooled, out=grads.buffer("out_linear.weight", P["out_linear.weight"]))
+    grads["out_linear.bias"] = ops.colsum(dlogits, out=grads.buffer("out_linear.bias", P["out_linear.bias"]))
     dpooled = ops.linear_dgrad(dlogits, P["out_linear.weight"])
     dy = ops.gp_maxpool_backward(dpooled, pooled, ctx["arg"], B, tail, n_img)     # through max + ReLU
     dy2 = dy.view(n_img * IMG_PIX, tail)
-    grads["c1x1_tail.bias"] = ops.colsum(dy2)
+    grads["c1x1_tail.bias"] = ops.colsum(dy2, out=grads.buffer("c1x1_tail.bias", P["c1x1_tail.bias"]))
     x_last = ctx["x_last"]
     # tail conv gradients: tail is tiny (<= 64 channels) -> fp32 SGEMMs
-    grads["c1x1_tail.weight"] = ops.linear_wgrad(dy2, x_last.view(n_img * IMG_PIX, C), ksplit=32).view(tail, C, 1, 1)
+    dwt = grads.buffer("c1x1_tail.weight", P["c1x1_tail.weight"])
+    ops.linear_wgrad(dy2, x_last.view(n_img * IMG_PIX, C), ksplit=32, out=dwt.view(tail, C))
+    grads["c1x1_tail.weight"] = dwt
     return ops.linear_dgrad(dy2, P["c1x1_tail.weight"].view(tail, C)).view(n_img, IMG_PIX, C)
 
 
@@ -483,10 +508,10 @@ def tmh_generator_backward(P, cache, ctx, dfilm, q_input, q_lens32, sink):
     hvec, W = ctx["hvec"], ctx["W"]
     H = hvec.shape[-1]
     N = 2 * C * nb
-    dgam = torch.zeros(N, device=dev, dtype=torch.float32)
-    dbet = torch.zeros(N, device=dev, dtype=torch.float32)
-    dw_out = torch.zeros_like(P["fc_attn_out.weight"])
-    db_out = torch.zeros(N, device=dev, dtype=torch.float32)
+    dgam = sink.buffer("decoder_norm.weight", P["decoder_norm.weight"])
+    dbet = sink.buffer("decoder_norm.bias", P["decoder_norm.bias"])
+    dw_out = sink.buffer("fc_attn_out.weight", P["fc_attn_out.weight"])
+    db_out = sink.buffer("fc_attn_out.bias", P["fc_attn_out.bias"])
     dhvec = torch.empty_like(hvec)
     for k in range(nb):
         dcond = ops.ln_slice_backward(ctx["conds"][k], P["decoder_norm.weight"], plan.film_row, dfilm, 2 * k * C, 2 * C,
@@ -498,10 +523,10 @@ def tmh_generator_backward(P, cache, ctx, dfilm, q_input, q_lens32, sink):
     sink["decoder_norm.bias"] = dbet
     sink["fc_attn_out.weight"] = dw_out
     sink["fc_attn_out.bias"] = db_out
-    dw_att = torch.zeros_like(P["fc_hidden_attn.weight"])
-    db_att = torch.zeros_like(P["fc_hidden_attn.bias"])
-    deg = torch.zeros(H, device=dev, dtype=torch.float32)
-    deb = torch.zeros(H, device=dev, dtype=torch.float32)
+    dw_att = sink.buffer("fc_hidden_attn.weight", P["fc_hidden_attn.weight"])
+    db_att = sink.buffer("fc_hidden_attn.bias", P["fc_hidden_attn.bias"])
+    deg = sink.buffer("encoder_norm.weight", P["encoder_norm.weight"])
+    deb = sink.buffer("encoder_norm.bias", P["encoder_norm.bias"])
     dstates = ops.tmh_hops_backward(ctx["states"], ctx["h_pass"], plan.img_frame, plan.img_clip, q_lens32, W, nb,
                                     P["encoder_norm.weight"], P["fc_hidden_attn.weight"], hvec, ctx["enc_out"],
                                     ctx["enc_stat"], ctx["coefs"], dhvec, dw_att, db_att, deg, deb)
@@ -524,8 +549,8 @@ def tmh_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens_host, q_lens
     return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
 
 
-def tmh_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None):
-    grads = GradSink(grad_hook)
+def tmh_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None, grad_bucket=None):
+    grads = GradSink(grad_hook, grad_bucket)
     dx_last = _gp_tail_backward(P, ctx, dlogits, grads)
     trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=tmh_generator_backward, mask_relu=False)
     return grads

@@ -39,12 +39,29 @@ class _FilmFunction(torch.autograd.Function):
         mod = ctx.mod
         if dlogits is None:
             return (None,) * (6 + len(mod._param_names))
+        bucket = getattr(mod, "_grad_bucket", None)
+        if bucket:
+            # flat-bucket mode (videonavqa_b200.optim.FlatBuffers): one memset, the kernels write every registered
+            # parameter's gradient into its slice, the reducer / optimizer consume the bucket in place
+            mod._grad_flat.zero_()
         grads = mod._backward_impl(ctx.P, ctx.saved, dlogits)
         hook = getattr(mod, "_grad_hook", None)
         if hook is not None and hasattr(hook, "wait"):
             hook.wait()     # in-flight gradient all-reduces (videonavqa_b200.dp) must land before autograd reads them
         ctx.saved = None
-        return (None,) * 6 + tuple(grads.get(n) for n in mod._param_names)
+        out = []
+        for n in mod._param_names:
+            g = grads.get(n)
+            if bucket and n in bucket and g is not None:
+                # p.grad IS the bucket slice (no copy by AccumulateGrad).  Overwrite semantics: the reference zeroes
+                # the gradients every iteration (eval/q_and_v_eval.py:139); accumulation across backward calls is
+                # not supported in this mode.
+                ctx.P[n].grad = bucket[n]
+                g = None
+            out.append(g)
+        if bucket:
+            mod._bucket_filled = True
+        return (None,) * 6 + tuple(out)
 
 
 def check_channels(num_input_channels, num_res_block_channels, hidden_size):
@@ -84,6 +101,8 @@ class FilmModuleBase(nn.Module):
         fh = getattr(self, "film_hidden", None)
         if fh is not None:
             self.film_hidden = (fn(fh[0]), fn(fh[1]))
+        if "_weight_cache" in self.__dict__:
+            self.invalidate_weight_cache()
         return out
 
     def init_hidden(self):
@@ -122,7 +141,7 @@ class FilmModuleBase(nn.Module):
         q_lens_dev = q_lens.to(dev).long()
         q_lens32 = q_lens_dev.to(torch.int32)
         # film_hidden is kept in q_len-sorted order like the reference (film_attn_pt_stem.py:153-160)
-        perm = q_lens_dev.sort(0, descending=True)[1]
+        perm = q_lens_dev.sort(0, descending=True, stable=True)[1]
         h = torch.empty(self.batch_size, self.hidden_size, device=dev)
         c = torch.empty_like(h)
         h[perm] = self.film_hidden[0][0].to(dev).detach()
@@ -135,6 +154,20 @@ class FilmModuleBase(nn.Module):
 
     def _finish(self, perm, h, c):
         self.film_hidden = (h[perm].unsqueeze(0), c[perm].unsqueeze(0))
+
+    def invalidate_weight_cache(self, registered_only=False):
+        """Drop the packed-weight caches (engine.WeightCache).  Needed after the parameters were written through
+        ``.data`` or raw pointers (weight broadcasts, reference-style ``m.weight.data.fill_()``, the fused optimizer):
+        those writes do not bump the autograd version counter the cache keys on."""
+        if registered_only:
+            self._cache.invalidate(list(self.parameters()))
+        else:
+            self._cache.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_weight_cache()
+        return out
 
     @property
     def _cache(self):

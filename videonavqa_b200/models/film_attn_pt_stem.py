@@ -75,4 +75,5 @@ class FiLMAttnPretrainedStem(FilmModuleBase):
         if "y0" not in ctx:
             raise RuntimeError("backward through the B200 FiLM path needs train() mode (BatchNorm batch statistics)")
         return engine.attn_backward(P, self._cache, ctx, dlogits, ctx["q_in"], ctx["q_lens32"],
-                                    grad_hook=getattr(self, "_grad_hook", None))
+                                    grad_hook=getattr(self, "_grad_hook", None),
+                                    grad_bucket=getattr(self, "_grad_bucket", None))

@@ -103,10 +103,12 @@ def pack_matrix(w, transpose=False):
     return pack_conv_weight(w.view(n, k, 1, 1), transpose_flip=transpose)[0]
 
 
-def permute_fc_weight(w, C, inverse=False, n_pad=None):
+def permute_fc_weight(w, C, inverse=False, n_pad=None, out=None):
     n = w.shape[0]
     n_pad = n if inverse else (n_pad or round_up(n, 128))
-    out = torch.empty(n if inverse else n_pad, C * IMG_PIX, device=w.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(n if inverse else n_pad, C * IMG_PIX, device=w.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.numel() == (n if inverse else n_pad) * C * IMG_PIX
     check(_lib.lib().vnqa_permute_fc_weight(_p(_f32c(w)), _p(out), n, n_pad, C, int(inverse), _stream()),
           "permute_fc_weight")
     return out
