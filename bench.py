@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--ragged", action="store_true", help="ragged v_lens (secondary config) instead of all 35")
     ap.add_argument("--cpu-clips", type=int, default=4, help="clips in the bounded CPU sample (~10 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--candidate-fp16", action="store_true",
-                    help="A/B only: route the model through experimental/f16 (kind::f16 operands); not the product path")
+    ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
+                    help="fused = videonavqa_b200.optim.FusedClipAdam over the flat bucket; torch = clip_grad_norm_ + Adam")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager baseline on the same GPU")
     return ap.parse_args()
 
 
@@ -136,10 +137,12 @@ class ClockSampler(threading.Thread):
 def summarise_kernels(klass, steps, ms_per_step):
     """klass: tag -> [total_ms, launches, work per launch] (flops, or bytes for tags starting with 'hbm.')."""
     out = {}
-    for tag, (tot, n, work) in sorted(klass.items(), key=lambda kv: -kv[1][0]):
+    for tag, (tot, n, work, each) in sorted(klass.items(), key=lambda kv: -kv[1][0]):
         if n == 0 or tot <= 0:
             continue
+        each = sorted(each)
         e = {"launches_per_step": n // max(steps, 1), "ms_per_launch": round(tot / n, 4),
+             "ms_min_med_max": [round(each[0], 4), round(each[len(each) // 2], 4), round(each[-1], 4)],
              "share_of_step": round(tot / max(steps, 1) / ms_per_step, 4)}
         if tag.startswith("hbm."):
             e["gb_per_s"] = round(work / (tot / n) * 1e-6, 1)
@@ -199,11 +202,47 @@ def start_watchdog():
     t.start()
 
 
+def eager_gpu_leg(dev, B, steps=2):
+    """The reference ALGORITHM (oracle code = same per-frame loop of nn.functional calls -> cuDNN / cuBLAS) run eagerly
+    on the same B200, fp32 and with TF32 enabled: the 'what would stock PyTorch do on this box' bar.
+    Checker / baseline tooling only."""
+    import torch
+    from oracle import film_oracle as O
+    p = {k: t.to(dev) for k, t in O.init_params("attn", seed=1).items()}
+    v, q, v_lens, q_lens, labels = [t.to(dev) for t in O.synthetic_batch(B, seed=0)]
+    out = {"what": "PyTorch eager (oracle code on the same GPU), FiLM-attn fwd+bwd without optimizer", "batch": B}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = True
+
+            def step():
+                O.loss_and_grads("attn", p, {k: t.to(dev) for k, t in O.new_bn_state(CFG["C"]).items()},
+                                 tuple(t.to(dev) for t in O.new_film_state(B, CFG["hidden"])), v, q, v_lens, q_lens,
+                                 labels, training=True)
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {"ms_per_step": round(ms, 2), "clips_per_s": round(B / ms * 1e3, 2)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    return out
+
+
 def gpu_leg(args):
     _log("importing torch")
     import torch
     import torch.distributed as dist
     from videonavqa_b200 import dp, ops
+    from videonavqa_b200.optim import FusedClipAdam
     from videonavqa_b200.synth import synthetic_batch
     from videonavqa_b200.models import (FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem,
                                         TimeMultiHopFiLMPretrainedStem)
@@ -213,7 +252,7 @@ def gpu_leg(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     # stall monitor (tools/hangwatch.py): a wedged rank reports where it is wedged and exits instead of waiting for
-    # the NCCL watchdog.  On by default for multi-GPU runs; BENCH_TRACE=1 also keeps one CUDA event per launch.
+    # a collective watchdog.  On by default for multi-GPU runs; BENCH_TRACE=1 also keeps one CUDA event per launch.
     stall_s = float(os.environ.get("BENCH_HANGWATCH_S", "90" if world > 1 else "0"))
     beat = lambda what="": None     # noqa: E731
     if stall_s > 0:
@@ -226,11 +265,12 @@ def gpu_leg(args):
             ops.TRACE = collections.deque(maxlen=1200)
     dev = torch.device("cuda", local)
     if world > 1:
-        _log("init_process_group")
-        # a lost rank must end the job with an error, not hang the box: NCCL's watchdog aborts after the timeout
-        dist.init_process_group("nccl", device_id=dev,
-                                timeout=datetime.timedelta(seconds=int(os.environ.get("BENCH_NCCL_TIMEOUT_S", "240"))))
-    _log("process group ready; building model")
+        _log("rendezvous (gloo) + NCCL communicator of libvnqa_b200")
+        # torch.distributed is the host-side rendezvous only (NCCL id exchange, CPU barrier, max-over-ranks of the
+        # timings); the gradient all-reduce runs on the library's own NCCL communicator (videonavqa_b200.dp)
+        dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=int(os.environ.get("BENCH_PG_TIMEOUT_S", "600"))))
+        dp.init(rank, world)
+    _log("communicator ready; building model")
     B = args.batch
     torch.manual_seed(1)
     M = MODELS[args.model]
@@ -244,19 +284,26 @@ def gpu_leg(args):
     else:
         model = TimeMultiHopFiLMPretrainedStem(num_tail_channels=M["tail"], **common)
     model = model.to(dev)
-    if args.candidate_fp16:
-        sys.path.insert(0, os.path.join(ROOT, "experimental", "f16"))
-        import engine_f16
-        engine_f16.install(model)
-    reducer = None
-    _log("model on device")
-    if world > 1:
-        dp.broadcast_module(model)
-        _log("weights broadcast")
-        reducer = dp.GradAllReducer(model)
     train = args.workload == "train"
     model.train(train)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4) if train else None        # eval.sh:16
+    reducer = None
+    opt = None
+    fused = train and args.optimizer == "fused"
+    if train:
+        # eval.sh:16 (Adam, lr 1e-4) + q_and_v_eval.py:137 (clip_grad_norm 1.0): fused over flat buffers by default,
+        # --optimizer torch = the reference's own two calls (A/B)
+        if fused:
+            opt = FusedClipAdam(model.parameters(), lr=1e-4, max_norm=1.0).attach(model)
+        else:
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    _log("model on device")
+    if world > 1:
+        if train and not fused:
+            raise SystemExit("data-parallel training needs --optimizer fused (flat gradient bucket)")
+        dp.broadcast_module(model, opt.flat if fused else None)
+        _log("weights broadcast")
+        if train:
+            reducer = dp.FlatReducer(model, opt.flat)
 
     # synthetic clips, a different shard per rank; kept in pinned host memory for the e2e leg
     v, q, v_lens, q_lens, labels = synthetic_batch(B, c_in=CFG["c_in"], T=CFG["T"], Lq=CFG["Lq"], vocab=CFG["vocab"],
@@ -266,6 +313,7 @@ def gpu_leg(args):
     _log("host batch pinned")
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
     n_frames_total = int(v_lens.sum())
+    opt_launches = [0]
 
     def step(dv, dq, dvl, dql, dlab):
         beat("step")
@@ -276,16 +324,19 @@ def gpu_leg(args):
         out = model(dv, dq, dvl, dql)
         loss = torch.nn.functional.cross_entropy(out, dlab, reduction="sum")       # eval.sh:15
         loss.backward()                                                            # all-reduce overlapped inside
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                    # q_and_v_eval.py:137
+        if not fused:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)                # q_and_v_eval.py:137
+        else:
+            opt_launches[0] += 2
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
 
     def barrier():
         beat("barrier")
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
         beat("barrier done")
 
     # ---------------- device-resident timing
@@ -302,6 +353,7 @@ def gpu_leg(args):
         sampler.start()
     ops.PROFILE = []
     launches0 = ops.LAUNCHES
+    opt_launches[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -310,66 +362,91 @@ def gpu_leg(args):
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     _log(f"device-resident timing done: {ms:.2f} ms/step")
-    launches = (ops.LAUNCHES - launches0) // args.steps
+    launches = (ops.LAUNCHES - launches0 + opt_launches[0]) // args.steps
     prof, ops.PROFILE = ops.PROFILE, None
     if rank == 0:
         sampler.stop()
     # per-kernel-class durations from the in-region events
     klass = {}
     for tag, flops, a, b in prof:
-        d = klass.setdefault(tag, [0.0, 0, flops])
-        d[0] += a.elapsed_time(b); d[1] += 1
+        d = klass.setdefault(tag, [0.0, 0, flops, []])
+        t = a.elapsed_time(b)
+        d[0] += t; d[1] += 1; d[3].append(t)
 
-    # ---------------- end-to-end timing: host inputs every step, prefetched on a copy stream, loss read back
+    # ---------------- end-to-end timing: host inputs every step (pinned memory), prefetched on a copy stream into a
+    # double buffer while the previous step computes; the loss is read back every step
     copy_stream = torch.cuda.Stream(device=dev)
+    prefetch = os.environ.get("BENCH_E2E_PREFETCH", "1") != "0"
+    slots = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    slot_free = [None, None]      # event: the step that consumed this slot has been enqueued and finished on the GPU
 
-    # N > 1: the inputs are copied on the compute stream (no prefetch stream) - see DESIGN.md §4
-    prefetch = world == 1 and os.environ.get("BENCH_E2E_PREFETCH", "1") != "0"
-
-    def fetch():
+    def fetch(k):
+        dst = slots[k % 2]
         if not prefetch:
-            return [x.to(dev, non_blocking=True) for x in host], None
+            for d, h in zip(dst, host):
+                d.copy_(h, non_blocking=True)
+            return dst, None
+        if slot_free[k % 2] is not None:
+            copy_stream.wait_event(slot_free[k % 2])
         with torch.cuda.stream(copy_stream):
-            t = [x.to(dev, non_blocking=True) for x in host]
+            for d, h in zip(dst, host):
+                d.copy_(h, non_blocking=True)
             ev = torch.cuda.Event(); ev.record(copy_stream)
-        return t, ev
+        return dst, ev
 
     def consume(item):
         t, ev = item
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
-            for x in t:
-                x.record_stream(torch.cuda.current_stream())
         return t
 
+    def release(k):
+        ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream())
+        slot_free[k % 2] = ev
+
     for i in range(2):
-        r = step(*consume(fetch()))
+        t = consume(fetch(i))
+        r = step(t[0], t[1], host[2], host[3], t[4])      # lengths stay on the host: no device read in forward
+        release(i)
         _ = r.detach().sum().item()
         _log(f"e2e warm-up step {i} done")
     barrier()
     d2h = 4 if train else B * CFG["classes"] * 4
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    nxt = fetch()
+    nxt = fetch(0)
     for i in range(args.steps):
         t = consume(nxt)
         if i + 1 < args.steps and prefetch:
-            nxt = fetch()                      # overlaps with this step's compute
-        r = step(*t)
+            nxt = fetch(i + 1)                 # overlaps with this step's compute
+        r = step(t[0], t[1], host[2], host[3], t[4])
+        release(i)
         _ = r.detach().sum().item() if train else r.cpu()     # device->host read of the step result
         if i + 1 < args.steps and not prefetch:
-            nxt = fetch()
+            nxt = fetch(i + 1)
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1) / args.steps
     _log(f"e2e timing done: {e2e_ms:.2f} ms/step")
 
+    dp_check = None
     if world > 1:
-        tt = torch.tensor([ms, e2e_ms], device=dev)
+        tt = torch.tensor([ms, e2e_ms], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(tt[0]), float(tt[1])
+        if reducer is not None:
+            # the exchange itself, outside the timed region: one more backward with the reducer's result kept, then
+            # every rank's reduced checksum must be identical and equal the sum of the per-rank local checksums
+            model._grad_hook = None
+            model.init_hidden()
+            loss = torch.nn.functional.cross_entropy(model(*dev_in[:4]), dev_in[4], reduction="sum")
+            loss.backward()
+            dp_check = dp.verify_allreduce(opt.flat)
+            dp_check["allreduce_calls_per_step"] = reducer.last_calls
+            torch.cuda.synchronize()
     if rank != 0:
         if world > 1:
+            dp.shutdown()
             dist.destroy_process_group()
         return None
 
@@ -381,7 +458,7 @@ def gpu_leg(args):
     bf16_peak = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)"
                 if peaks else "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)")
-    tf32_peak = bf16_peak if args.candidate_fp16 else bf16_peak / 2.0      # kind::f16 issues at the bf16 rate
+    tf32_peak = bf16_peak / 2.0
     dom_tag = f"conv_gemm.9tap.epi3.k{CFG['C']}.n{CFG['C']}"            # conv3x3 + FiLM epilogue (forward)
     kernels = summarise_kernels(klass, args.steps, ms)
     roof = None
@@ -407,17 +484,18 @@ def gpu_leg(args):
         "metric": metric_name(args),
         "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": ("fp16 operands/activations (experimental/f16 candidate), fp32 accumulate"
-                                        if args.candidate_fp16 else "tf32 operands, fp32 accumulate/storage"),
+        "vs_baseline": None, "dtype": "tf32 operands, fp32 accumulate/storage",
         "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "global_batch": clips, "frames_per_clip": CFG["T"], "parallelism": f"dp{world}",
-                   "step": "fwd+CE(sum)+bwd" + ("+allreduce(sum)" if world > 1 else "") + "+clip_grad_norm+Adam" if train
+                   "step": ("fwd+CE(sum)+bwd" + ("+allreduce(sum, overlapped)" if world > 1 else "") +
+                            ("+fused clip_grad_norm/Adam" if fused else "+clip_grad_norm+Adam")) if train
                    else "eval forward", "l2": "inputs larger than L2 (v_input 596 MB, activations 1.19 GB each)",
                    "frame_images_per_step": n_frames_total * world},
         "model_tflops": round(clips * gflop * scale / ms, 1),
         "e2e": {"value": round(clips / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3)},
+                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3),
+                "how": "pinned host batch -> double-buffered device inputs on a copy stream, loss.item() every step"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": roof,
@@ -425,9 +503,16 @@ def gpu_leg(args):
         "kernels": kernels,
     }
     if reducer is not None:
-        out["allreduce_bytes_per_step"] = getattr(reducer, "last_bytes", None)
+        out["allreduce_bytes_per_step"] = reducer.last_bytes
+        out["dp_check"] = dp_check
     if world > 1:
+        dp.shutdown()
         dist.destroy_process_group()
+    if world == 1 and train and args.model == "attn" and not args.no_eager:
+        try:
+            out["gpu_eager_baseline"] = eager_gpu_leg(dev, B)
+        except Exception as e:  # noqa: BLE001
+            out["gpu_eager_baseline"] = {"error": repr(e)[:200]}
     return out
 
 

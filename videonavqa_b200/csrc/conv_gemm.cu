@@ -251,7 +251,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // the cluster lands on SMs that other work has just vacated (a persistent grid sharing the GPU with another
   // stream); an alloc issued before the peer was up wedged the peer's own alloc for good (round-2 probe,
   // profiles/r02_dp_hang_rootcause.md).  Hence: cluster barrier, THEN alloc, then the usual fence/barrier/fence.
+#ifndef VNQA_NO_TMEM_FIX   /* A/B switch for the soak test of the fix (make nofix); never defined in the product */
   if (NCTA == 2) cluster_sync_all();
+#endif
   if (warp == 2) {
     if (NCTA == 2) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
     else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -376,7 +378,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
   // neither CTA of a pair leaves (and frees its SM for the next cluster) before BOTH have released their tensor memory
+#ifndef VNQA_NO_TMEM_FIX
   if (NCTA == 2) cluster_sync_all();
+#endif
 }
 
 template <int EPI, int NCTA>

@@ -65,7 +65,8 @@ def init(rank=None, world=None):
         _lib.check(L.vnqa_nccl_unique_id(buf), "vnqa_nccl_unique_id")
         box[0] = buf.raw
     dist.broadcast_object_list(box, src=0)
-    _lib.check(L.vnqa_nccl_init(ctypes.c_char_p(box[0]), rank, world), "vnqa_nccl_init")
+    idbuf = ctypes.create_string_buffer(bytes(box[0]), 128)
+    _lib.check(L.vnqa_nccl_init(idbuf, rank, world), "vnqa_nccl_init")
     _READY[0] = True
 
 

@@ -69,6 +69,23 @@ class Plan:
         self.frame_ct_host = frame_ct
 
 
+_PLANS = {}
+
+
+def get_plan(v_lens_host, B, T, device):
+    """Plans are pure functions of (v_lens, B, T): keep the last few (their index arrays are read-only device tensors),
+    so a loop over same-shaped batches neither rebuilds them nor copies them to the device again."""
+    dev = torch.device(device)
+    key = (tuple(int(x) for x in v_lens_host), B, T, dev.type, dev.index if dev.index is not None else
+           (torch.cuda.current_device() if dev.type == "cuda" else -1))
+    plan = _PLANS.get(key)
+    if plan is None:
+        if len(_PLANS) >= 16:
+            _PLANS.pop(next(iter(_PLANS)))
+        plan = _PLANS[key] = Plan(v_lens_host, B, T, device)
+    return plan
+
+
 class GradSink(dict):
     """name -> gradient.  ``buffer(name, like)`` hands out the tensor a gradient is written into: a view of the flat
     gradient bucket when one is installed (videonavqa_b200.optim.FlatBuffers - zeroed once at the start of backward,
@@ -346,7 +363,7 @@ def attn_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, 
     """FiLMAttnPretrainedStem.forward (models/film_attn_pt_stem.py:188-301)."""
     dev = v_input.device
     B = v_input.shape[0]
-    plan = Plan(v_lens_host, B, T, dev)
+    plan = get_plan(v_lens_host, B, T, dev)
     x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
     C, n_img = ctx["C"], plan.n_img
     A = P["fc_attn_1.weight"].shape[1]
@@ -423,7 +440,7 @@ def gp_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, fi
     """FiLMGlobalPoolingPretrainedStem.forward (models/film_global_pooling_pt_stem.py:180-238)."""
     dev = v_input.device
     B, T = v_input.shape[0], v_input.shape[-1]
-    plan = Plan(v_lens_host, B, T, dev)
+    plan = get_plan(v_lens_host, B, T, dev)
     x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
     return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
 
@@ -471,7 +488,7 @@ def _gp_tail_backward(P, ctx, dlogits, grads):
 
 
 # ======================================================================================== multi-hop model
-def tmh_generator_forward(P, cache, plan, q_input, q_lens32, film_h, film_c, save, nb, C):
+def tmh_generator_forward(P, cache, plan, q_input, q_lens32, film_h, film_c, save, nb, C, max_q_len=None):
     """compute_film_encoding + decode_to_film_values of TimeMultiHopFiLMPretrainedStem
     (models/time_multi_hop_pt_stem.py:124-184) for every frame image at once."""
     enc = "q_encoder."
@@ -482,7 +499,7 @@ def tmh_generator_forward(P, cache, plan, q_input, q_lens32, film_h, film_c, sav
     c0 = film_c.clone() if save else None
     h_pass, sg, sc, sh, states = ops.lstm_chain_forward(gx, q_lens32, whh_t, film_h, film_c, plan.n_frames, save=save,
                                                         want_states=True)
-    W = plan.max_q_len                       # pad_packed_sequence pads to the longest question of the batch (:136)
+    W = max_q_len                            # pad_packed_sequence pads to the longest question of the batch (:136)
     hvec, enc_out, enc_stat, coefs = ops.tmh_hops_forward(
         states, h_pass, plan.img_frame, plan.img_clip, W, nb, P["encoder_norm.weight"], P["encoder_norm.bias"],
         P["fc_hidden_attn.weight"], P["fc_hidden_attn.bias"])
@@ -542,10 +559,10 @@ def tmh_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens_host, q_lens
     multi-hop FiLM generator, then the global-pooling tail."""
     dev = v_input.device
     B, T = v_input.shape[0], v_input.shape[-1]
-    plan = Plan(v_lens_host, B, T, dev)
-    plan.max_q_len = int(max(q_lens_host))
+    plan = get_plan(v_lens_host, B, T, dev)
+    max_q_len = int(max(q_lens_host))
     x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save,
-                           gen_fwd=tmh_generator_forward)
+                           gen_fwd=lambda *a: tmh_generator_forward(*a, max_q_len=max_q_len))
     return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
 
 

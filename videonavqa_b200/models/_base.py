@@ -130,17 +130,34 @@ class FilmModuleBase(nn.Module):
         need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
         return _FilmFunction.apply(self, need_grad, v_input.float().contiguous(), q_input, v_lens, q_lens, *tensors)
 
-    def _prepare(self, v_input, q_input, v_lens, q_lens):
-        dev = v_input.device
+    def _host_lens(self, v_lens, q_lens, dev):
+        """Clip / question lengths on the host.  The reference reads them from the device >= 70 times per forward
+        (models/film_attn_pt_stem.py:159,203); here: no device read at all when the caller passes CPU tensors (they
+        come from the DataLoader on the host), otherwise ONE read - skipped when the same, unmodified tensors were
+        passed to the previous call (a training loop re-using its length tensors never waits for the GPU here)."""
+        if not v_lens.is_cuda and not q_lens.is_cuda:
+            return v_lens.tolist(), q_lens.tolist()
+        key = (id(v_lens), v_lens._version, v_lens.data_ptr(), id(q_lens), q_lens._version, q_lens.data_ptr())
+        hit = self.__dict__.get("_lens_cache")
+        if hit is not None and hit[0] == key and hit[1]() is v_lens and hit[2]() is q_lens:
+            return hit[3], hit[4]
         lens = torch.stack([v_lens.to(dev).long(), q_lens.to(dev).long()]).cpu()     # the one host sync
         v_host, q_host = lens[0].tolist(), lens[1].tolist()
+        import weakref
+        self.__dict__["_lens_cache"] = (key, weakref.ref(v_lens), weakref.ref(q_lens), v_host, q_host)
+        return v_host, q_host
+
+    def _prepare(self, v_input, q_input, v_lens, q_lens):
+        dev = v_input.device
+        v_host, q_host = self._host_lens(v_lens, q_lens, dev)
         L = q_input.shape[1]
         if min(q_host) < 1 or max(q_host) > L:
             raise ValueError(f"q_lens must lie in [1, {L}]")
         self._last_q_host = q_host
-        q_lens_dev = q_lens.to(dev).long()
+        q_lens_dev = q_lens.to(dev, non_blocking=True).long()
         q_lens32 = q_lens_dev.to(torch.int32)
-        # film_hidden is kept in q_len-sorted order like the reference (film_attn_pt_stem.py:153-160)
+        # film_hidden is kept in q_len-sorted order like the reference (film_attn_pt_stem.py:153-160); stable, so that
+        # clips with equal question lengths keep their order across calls
         perm = q_lens_dev.sort(0, descending=True, stable=True)[1]
         h = torch.empty(self.batch_size, self.hidden_size, device=dev)
         c = torch.empty_like(h)
