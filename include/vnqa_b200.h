@@ -212,13 +212,13 @@ int vnqa_attn_tail_backward(const float* feats, const int32_t* v_lens, int32_t n
  * vnqa_sumsq_partials writes vnqa_opt_num_partials() per-block sums of g^2 (fp64, no atomics -> deterministic);
  * vnqa_clip_adam reduces them in a fixed order, scales the gradient by grad_scale * min(1, max_norm / (norm + 1e-6))
  * (max_norm <= 0: no clipping, partials may be NULL) and applies torch.optim.Adam's update (no amsgrad, no weight
- * decay) with the host-computed bias corrections 1 - beta1^t and sqrt(1 - beta2^t).  norm_out (optional) receives
+ * decay) for step number `step` (1-based; bias corrections and 1 - beta formed in double on the host like PyTorch).  norm_out (optional) receives
  * the total gradient norm that clip_grad_norm_ would return. */
 int vnqa_opt_num_partials(void);
 int vnqa_sumsq_partials(const float* g, int64_t n, double* partials, void* stream);
 int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const double* partials, int32_t n_partials,
-                   float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
-                   float bias_correction1, float bias_correction2_sqrt, float* norm_out, void* stream);
+                   float grad_scale, float max_norm, double lr, double beta1, double beta2, double eps, int64_t step,
+                   float* norm_out, void* stream);
 
 /* ---- K10 (new - the reference is single-GPU): gradient all-reduce over NVLink / NVSwitch.
  * One process per GPU owns one ncclComm_t and one dedicated communication stream inside the library.  NCCL is

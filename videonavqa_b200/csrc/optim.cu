@@ -8,6 +8,8 @@
 //                                 and applies torch.optim.Adam's update (no amsgrad, no weight decay):
 //                                 m += (1-b1)(g-m);  v = b2 v + (1-b2) g^2;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // Algorithmic traffic: pass 1 reads 4 B/element, pass 2 reads 16 B and writes 12 B per element.
+#include <cmath>
+
 #include "common.h"
 
 namespace vnqa {
@@ -43,8 +45,8 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adam_kernel(float4* __restri
                                                                 float4* __restrict__ m, float4* __restrict__ v,
                                                                 long long n4, const double* __restrict__ partials,
                                                                 int n_partials, float grad_scale, float max_norm,
-                                                                float lr, float beta1, float beta2, float eps,
-                                                                float bias_correction1, float bias_correction2_sqrt,
+                                                                float step_size, float beta2, float w1, float w2,
+                                                                float eps, float bias_correction2_sqrt,
                                                                 float* __restrict__ norm_out) {
   // every block sums the same partials in the same order -> identical coef everywhere, run to run
   __shared__ double red[OPT_THREADS];
@@ -63,8 +65,6 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adam_kernel(float4* __restri
     coef *= c < 1.f ? c : 1.f;
     if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out != nullptr) *norm_out = total_norm;
   }
-  const float step_size = lr / bias_correction1;
-  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 gi = __ldg(g + i);
     float4 mi = m[i], vi = v[i], pi = p[i];
@@ -103,9 +103,13 @@ extern "C" int vnqa_sumsq_partials(const float* g, int64_t n, double* partials, 
 }
 
 extern "C" int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const double* partials,
-                              int32_t n_partials, float grad_scale, float max_norm, float lr, float beta1, float beta2,
-                              float eps, float bias_correction1, float bias_correction2_sqrt, float* norm_out,
-                              void* stream) {
+                              int32_t n_partials, float grad_scale, float max_norm, double lr, double beta1,
+                              double beta2, double eps, int64_t step, float* norm_out, void* stream) {
+  // scalar coefficients exactly as torch.optim.Adam forms them: in double on the host, rounded to fp32 once
+  VNQA_REQUIRE(step >= 1, "vnqa_clip_adam: step counts from 1");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1), bias_correction2_sqrt = (float)sqrt(bc2);
+  const float w1 = (float)(1.0 - beta1), w2 = (float)(1.0 - beta2);
   VNQA_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, "vnqa_clip_adam: need non-empty buffers of 4k floats");
   VNQA_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                  reinterpret_cast<uintptr_t>(v)) & 15) == 0, "vnqa_clip_adam: buffers must be 16-byte aligned");
@@ -114,8 +118,8 @@ extern "C" int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int6
   if (sms <= 0) return -2;
   clip_adam_kernel<<<sms * 8, OPT_THREADS, 0, as_stream(stream)>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
-      reinterpret_cast<float4*>(v), n / 4, partials, n_partials, grad_scale, max_norm, lr, beta1, beta2, eps,
-      bias_correction1, bias_correction2_sqrt, norm_out);
+      reinterpret_cast<float4*>(v), n / 4, partials, n_partials, grad_scale, max_norm, step_size, (float)beta2, w1, w2,
+      (float)eps, bias_correction2_sqrt, norm_out);
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -158,7 +158,7 @@ class FilmModuleBase(nn.Module):
         q_lens32 = q_lens_dev.to(torch.int32)
         # film_hidden is kept in q_len-sorted order like the reference (film_attn_pt_stem.py:153-160); stable, so that
         # clips with equal question lengths keep their order across calls
-        perm = q_lens_dev.sort(0, descending=True, stable=True)[1]
+        perm = q_lens_dev.sort(dim=0, descending=True, stable=True)[1]
         h = torch.empty(self.batch_size, self.hidden_size, device=dev)
         c = torch.empty_like(h)
         h[perm] = self.film_hidden[0][0].to(dev).detach()

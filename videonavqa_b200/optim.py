@@ -15,7 +15,6 @@ and loads into / from a plain ``torch.optim.Adam`` (checkpoint envelope of eval/
 from __future__ import annotations
 
 import ctypes
-import math
 
 import torch
 
@@ -145,8 +144,8 @@ class FusedClipAdam(torch.optim.Adam):
         if self.max_norm > 0:
             _lib.check(L.vnqa_sumsq_partials(P(f.grad), f.total, P(self._partials), st), "vnqa_sumsq_partials")
         _lib.check(L.vnqa_clip_adam(P(f.param), P(f.grad), P(self._m), P(self._v), f.total, P(self._partials),
-                                    self._n_partials, 1.0, self.max_norm, g["lr"], beta1, beta2, g["eps"],
-                                    1.0 - beta1 ** t, math.sqrt(1.0 - beta2 ** t), P(self._norm), st), "vnqa_clip_adam")
+                                    self._n_partials, 1.0, self.max_norm, g["lr"], beta1, beta2, g["eps"], t,
+                                    P(self._norm), st), "vnqa_clip_adam")
         for p in f.params:
             self.state[p]["step"] += 1
         if self._module is not None:
