@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VNQA_ABI_VERSION 1
+#define VNQA_ABI_VERSION 2
 #define VNQA_IMG_H 10
 #define VNQA_IMG_W 13
 #define VNQA_IMG_PIX 130 /* hard-coded 130 = 10*13 in models/film_attn_pt_stem.py:56 */
@@ -42,15 +42,17 @@ int vnqa_debug_build(void);
 /* ---- K0: (B, C, 10, 13, T) fp32, T innermost  ->  frame-image-major NHWC [n_img][130][C].
  * Replaces the strided slice v_input[:ct, :, :, :, i] (models/film_attn_pt_stem.py:210).
  * img_of[b*T + t] is the image index of (clip b, frame t), or -1 when t >= v_lens[b]. */
-int vnqa_frames_to_nhwc(const float* v_input, float* x_out, const int32_t* img_of, int32_t B, int32_t C, int32_t T,
-                        void* stream);
+int vnqa_frames_to_nhwc(const float* v_input, void* x_out, const int32_t* img_of, int32_t B, int32_t C, int32_t T,
+                        int32_t act_dtype, void* stream);
 /* (no backward: v_input needs no gradient - the stem is frozen, eval/q_and_v_eval.py:101-110) */
 
 /* ---- weight packing (derived caches; PyTorch-native layouts stay the source of truth).
  * conv weight (Cout, Cin, kh, kw) -> [taps][rows_pad][Cin] K-major rows (zero rows for cout..rows_pad).
  * transpose_flip != 0 builds the data-gradient operand instead: [taps][rows_pad >= Cin][Cout] with taps mirrored. */
-int vnqa_pack_conv_weight(const float* w, float* packed, int32_t cout, int32_t cin, int32_t taps,
-                          int32_t rows_pad, int32_t transpose_flip, void* stream);
+int vnqa_pack_conv_weight(const float* w, void* packed, int32_t cout, int32_t cin, int32_t taps,
+                          int32_t rows_pad, int32_t transpose_flip, int32_t act_dtype, void* stream);
+/* out[i] = fp16(scale * in[i]): fp32 -> fp16 producers at the edge of the fp16 domain (d feats, packed Linear weights) */
+int vnqa_to_half(const float* in, void* out, int64_t n, float scale, void* stream);
 /* Linear weight (N, C*130) in NCHW-flatten order (col = c*130 + p, models/film_attn_pt_stem.py:244) ->
  * (n_pad, 130*C) in NHWC order (col = p*C + c); inverse != 0 maps a gradient (n rows) back. */
 int vnqa_permute_fc_weight(const float* w, float* out, int32_t n, int32_t n_pad, int32_t C, int32_t inverse,
@@ -69,22 +71,28 @@ enum {
   VNQA_EPI_PLAIN = 7             /* out = acc                                    dX of conv1x1 / Linear */
 };
 
+/* Operand / activation storage of the tensor-core kernels ("act" below): tf32 = fp32 storage holding tf32-representable
+ * values (kind::tf32 MMA); fp16 = half storage with the same 10-bit mantissa (kind::f16 MMA: twice the rate, half the
+ * bytes).  Accumulation is fp32 either way.  With fp16 the backward signals are stored multiplied by a power-of-two
+ * loss scale and every kernel that leaves the fp16 domain multiplies by grad_unscale = 1 / scale. */
+enum { VNQA_ACT_TF32 = 0, VNQA_ACT_FP16 = 1 };
+
 typedef struct {
-  /* operands */
-  const float* w_packed; /* [taps][rows_pad][cin] from vnqa_pack_conv_weight (flat: [rows_pad][cin*splits]) */
-  const float* x;        /* activations [n_img][130][cin] (conv) or [n_img][x_ld] (flat) */
+  /* operands ("act" = float or __half, see act_dtype) */
+  const void* w_packed;  /* act [taps][rows_pad][cin] from vnqa_pack_conv_weight (flat: [rows_pad][cin*splits]) */
+  const void* x;         /* act activations [n_img][130][cin] (conv) or [n_img][x_ld] (flat) */
   int32_t taps;          /* 1 or 9 */
-  int32_t cin;           /* reduction length per tap (per split when flat); multiple of 32 */
+  int32_t cin;           /* reduction length per tap (per split when flat); tf32: multiple of 32, fp16: of 8 */
   int32_t cout;          /* real output channels */
   int32_t rows_pad;      /* cout rounded up to 128 */
   int32_t n_img;         /* conv: images; flat: rows of x */
   int32_t flat;          /* 0: conv over 10x13 images; 1: plain GEMM */
-  int32_t x_ld;          /* flat only: row stride of x in floats (>= cin*splits) */
+  int32_t x_ld;          /* flat only: row stride of x in elements (>= cin*splits) */
   int32_t splits;        /* flat only: split-K factor */
   int32_t epi;
-  int32_t no_round;      /* != 0: store full fp32 (output does not feed an MMA) */
+  int32_t no_round;      /* tf32 only, != 0: store full fp32 (output does not feed an MMA) */
   /* epilogue operands (unused ones may be NULL) */
-  float* out;            /* [rows][cout] (PARTIAL: [splits][n_img][cout]) */
+  void* out;             /* act [rows][cout]; always fp32 for STATS and PARTIAL ([splits][n_img][cout]) and with out_f32 */
   const float* bias;     /* [cout] */
   const float* scale;    /* AFFINE: [cout] */
   const float* shift;    /* AFFINE: [cout] */
@@ -95,21 +103,25 @@ typedef struct {
   const int32_t* film_row; /* FILM: row of `film` for each image (= frame*B + clip) */
   int32_t film_ld;
   int32_t alpha_off;     /* FILM: alpha at [alpha_off + co], beta at [alpha_off + cout + co] */
-  const float* res;      /* FILM: residual input [rows][cout]; DGRAD_RES: ReLU mask source */
-  float* z_out;          /* FILM: optional pre-FiLM output z (training) */
-  const float* add;      /* DGRAD_RES: tensor added before masking (skip-path gradient) */
-  float* dbias;          /* DGRAD_RES: optional per-channel sum of the written gradient, atomically accumulated */
+  const void* res;       /* act. FILM: residual input [rows][cout]; DGRAD_RES: ReLU mask source */
+  void* z_out;           /* act. FILM: optional pre-FiLM output z (training) */
+  const void* add;       /* act. DGRAD_RES: tensor added before masking (skip-path gradient) */
+  float* dbias;          /* DGRAD_RES: optional; += grad_unscale * per-channel sum of the written gradient (atomic) */
+  int32_t act_dtype;     /* VNQA_ACT_TF32 / VNQA_ACT_FP16 */
+  int32_t out_f32;       /* fp16 only, BIAS_RELU / PLAIN: store fp32 (tensors that leave the fp16 domain) */
+  float grad_unscale;    /* 0 is read as 1 */
 } vnqa_conv_args;
 
 int vnqa_conv_gemm(const vnqa_conv_args* args, void* stream);
 
-/* ---- K4: weight gradient dW[co][ci][tap] = sum_rows dY[row][co] * X[row (+) tap][ci] on tcgen05 (MN-major
- * operands, split-K over pixels, fp32 atomic reduction).  Output layout is PyTorch's (Cout, Cin, kh, kw).
- * taps == 1: accumulates into dw, which must be zero-initialised (ws may be NULL).
- * taps == 9: accumulates into the zero-initialised workspace ws [9][cout][cin] and then overwrites dw.
- * flat != 0: plain dY^T X with dy [n_img][cout], x [n_img][cin]. */
-int vnqa_conv_wgrad(const float* dy, const float* x, float* dw, float* ws, int32_t n_img, int32_t cout, int32_t cin,
-                    int32_t taps, int32_t flat, void* stream);
+/* ---- K4: weight gradient dW[co][ci][tap] = grad_unscale * sum_rows dY[row][co] * X[row (+) tap][ci] on tcgen05
+ * (MN-major operands of type act_dtype, split-K over pixels, DETERMINISTIC turn-ordered fp32 reduction: two launches on
+ * the same operands give the same bits).  dw is OVERWRITTEN in PyTorch's (Cout, Cin, kh, kw) layout.
+ * ws: workspace of vnqa_conv_wgrad_ws_bytes() bytes whose leading *zero_bytes bytes (turn counters) must be zero on
+ * entry; the kernel leaves them zero again.  flat != 0: plain dY^T X with dy [n_img][cout], x [n_img][cin]. */
+int64_t vnqa_conv_wgrad_ws_bytes(int32_t cout, int32_t cin, int32_t taps, int64_t* zero_bytes);
+int vnqa_conv_wgrad(const void* dy, const void* x, float* dw, void* ws, int32_t n_img, int32_t cout, int32_t cin,
+                    int32_t taps, int32_t flat, int32_t act_dtype, float grad_unscale, void* stream);
 
 /* ---- small fp32 GEMM (FFMA, exact fp32): C = [C +] A B^T + bias, optional ReLU.  A(m,k) = a[m*a_rs + k*a_cs],
  * B(n,k) = b[n*b_rs + k*b_cs].  ksplit > 1 splits K over gridDim.z with atomic accumulation into C (C must be
@@ -129,21 +141,21 @@ int vnqa_bn_finalize_train(const double* stat_sum, const double* stat_sq, const 
 int vnqa_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                         float eps, int32_t C, float* scale, float* shift, void* stream);
 /* x = y * scale[frame] + shift[frame]   (scale/shift are [T][C]) */
-int vnqa_bn_apply(const float* y, float* x, const int32_t* img_frame, const float* scale, const float* shift,
-                  int32_t n_img, int32_t C, void* stream);
+int vnqa_bn_apply(const float* y, void* x, const int32_t* img_frame, const float* scale, const float* shift,
+                  int32_t n_img, int32_t C, int32_t act_dtype, void* stream);
 /* dy = BN-backward(dx) masked by the preceding ReLU (y > 0); dbias += sum dy; dgamma/dbeta accumulated. */
-int vnqa_bn_backward(const float* dx, const float* y, const int32_t* img_frame, const int32_t* frame_ct,
+int vnqa_bn_backward(const void* dx, const float* y, const int32_t* img_frame, const int32_t* frame_ct,
                      int32_t n_frames, const float* mean, const float* rstd, const float* gamma, int32_t n_img,
-                     int32_t C, float* s1, float* s2, float* dy, float* dbias, float* dgamma, float* dbeta,
-                     void* stream);
+                     int32_t C, float* s1, float* s2, void* dy, float* dbias, float* dgamma, float* dbeta,
+                     int32_t act_dtype, float grad_unscale, void* stream);
 
 /* ---- FiLM backward (autograd of :229-239): dz = alpha * dout * [alpha z + beta > 0]; dfilm rows get
  * dalpha/dbeta; mask_relu != 0 additionally applies the gradient of the FiLM generator's final ReLU (:179), i.e.
  * zero where alpha/beta == 0 (attention / global-pooling models; the multi-hop model has no such ReLU);
  * dbias += sum dz. */
-int vnqa_film_backward(const float* dout, const float* z, const float* film, const int32_t* film_row, int32_t film_ld,
-                       int32_t alpha_off, int32_t n_img, int32_t C, float* dz, float* dfilm, float* dbias,
-                       int32_t mask_relu, void* stream);
+int vnqa_film_backward(const void* dout, const void* z, const float* film, const int32_t* film_row, int32_t film_ld,
+                       int32_t alpha_off, int32_t n_img, int32_t C, void* dz, float* dfilm, float* dbias,
+                       int32_t mask_relu, int32_t act_dtype, float grad_unscale, void* stream);
 
 /* out[dst_row[r]][n] = bias[n] + sum_s partial[s][r][n] */
 int vnqa_splitk_reduce(const float* partial, int32_t splits, int32_t rows, int32_t N, const float* bias,

@@ -151,7 +151,7 @@ static int run_case(const Case& c) {
   CK(cudaMemset(ddb, 0, c.cout * 4));
   CK(cudaMemset(dsum, 0, (size_t)T * c.cout * 8));
   CK(cudaMemset(dsq, 0, (size_t)T * c.cout * 8));
-  CKV(vnqa_pack_conv_weight(dw, dwp, c.cout, K, c.taps, rows_pad, 0, nullptr));
+  CKV(vnqa_pack_conv_weight(dw, dwp, c.cout, K, c.taps, rows_pad, 0, VNQA_ACT_TF32, nullptr));
   // producers round MMA operands to tf32 (rna) - emulate that for the activation input; the pack kernel rounds w
   round_kernel<<<148 * 8, 256>>>(dx, (long long)rows * K);
   CK(cudaDeviceSynchronize());

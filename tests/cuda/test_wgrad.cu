@@ -58,14 +58,15 @@ static int run_case(const Case& c) {
   CK(cudaMalloc(&x, rows * c.cin * 4));
   const size_t wn = (size_t)c.cout * c.cin * c.taps;
   CK(cudaMalloc(&dw, wn * 4));
-  CK(cudaMalloc(&ws, wn * 4));
-  CK(cudaMemset(ws, 0, wn * 4));
+  const int64_t ws_bytes = vnqa_conv_wgrad_ws_bytes(c.cout, c.cin, c.taps, nullptr);
+  CK(cudaMalloc(&ws, ws_bytes));
+  CK(cudaMemset(ws, 0, ws_bytes));   // only the leading turn counters need it; the kernel leaves them zero
   fill_kernel<<<148 * 8, 256>>>(dy, rows * c.cout, 17u, 1.0f);
   fill_kernel<<<148 * 8, 256>>>(x, rows * c.cin, 99u, 1.0f);
-  CK(cudaMemset(dw, 0, wn * 4));
+  CK(cudaMemset(dw, 0xFF, wn * 4));   // garbage: the kernel overwrites dw
   CK(cudaDeviceSynchronize());
   fprintf(stderr, "[%s] inputs ready\n", c.name);
-  CKV(vnqa_conv_wgrad(dy, x, dw, ws, c.n_img, c.cout, c.cin, c.taps, c.flat, nullptr));
+  CKV(vnqa_conv_wgrad(dy, x, dw, ws, c.n_img, c.cout, c.cin, c.taps, c.flat, VNQA_ACT_TF32, 1.f, nullptr));
   CK(cudaDeviceSynchronize());
   fprintf(stderr, "[%s] wgrad done\n", c.name);
   const int ns = 512;
@@ -108,9 +109,9 @@ static int run_case(const Case& c) {
   if (c.iters > 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CKV(vnqa_conv_wgrad(dy, x, dw, ws, c.n_img, c.cout, c.cin, c.taps, c.flat, nullptr));
+    CKV(vnqa_conv_wgrad(dy, x, dw, ws, c.n_img, c.cout, c.cin, c.taps, c.flat, VNQA_ACT_TF32, 1.f, nullptr));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < c.iters; ++i) CKV(vnqa_conv_wgrad(dy, x, dw, ws, c.n_img, c.cout, c.cin, c.taps, c.flat, nullptr));
+    for (int i = 0; i < c.iters; ++i) CKV(vnqa_conv_wgrad(dy, x, dw, ws, c.n_img, c.cout, c.cin, c.taps, c.flat, VNQA_ACT_TF32, 1.f, nullptr));
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= c.iters;

@@ -27,12 +27,17 @@ def _strict_fp32():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def _rand(shape, seed, relu=False, scale=1.0):
+def _rand(shape, seed, relu=False, scale=1.0, act=0):
+    """Random tensor already representable in the operand type: (kernel operand, the same values as fp32)."""
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randn(shape, device="cuda", generator=g) * scale
     if relu:
         x = x.clamp_min_(0)
-    return O.tf32_round(x)
+    if act:
+        h = x.half()
+        return h, h.float()
+    x = O.tf32_round(x)
+    return x, x
 
 
 def _nchw(x, n_img, C):
@@ -50,101 +55,160 @@ WGRAD_CASES = [
     (1024, 1024, 9, 2240),      # ResBlock conv3x3 at the benchmark shape (64 clips x 35 frames)
     (1024, 512, 9, 2240),       # conv_init
     (1024, 1024, 1, 2240),      # ResBlock conv1x1
-    (1024, 1024, 9, 1237),      # ragged: n_img not a multiple of the 4-image TMA box
+    (1024, 1024, 9, 1237),      # ragged: n_img not a multiple of the 4 / 8-image TMA box
     (256, 256, 9, 37),          # smallest CTA-pair shape, one partial chunk
     (512, 256, 1, 101),
+    (160, 96, 9, 11),           # single-CTA kernel, channels completed by TMA zero fill
 ]
+ACTS = [pytest.param(0, id="tf32"), pytest.param(1, id="fp16")]
 
 
+@pytest.mark.parametrize("act", ACTS)
 @pytest.mark.parametrize("cout,cin,taps,n_img", WGRAD_CASES)
-def test_wgrad_cta_pair_full_tensor(cout, cin, taps, n_img):
+def test_wgrad_full_tensor_and_deterministic(cout, cin, taps, n_img, act):
     from videonavqa_b200 import ops
-    dy = _rand((n_img, 130, cout), 1, scale=0.05)
-    x = _rand((n_img, 130, cin), 2, relu=True)
+    scale = 4096.0 if act else 1.0                       # fp16 backward signals carry the loss scale
+    dy, dyf = _rand((n_img, 130, cout), 1, scale=0.05, act=act)
+    x, xf = _rand((n_img, 130, cin), 2, relu=True, act=act)
     k = 3 if taps == 9 else 1
-    dw = torch.zeros(cout, cin, k, k, device="cuda")
-    ops.conv_wgrad(dy, x, dw, n_img=n_img, cout=cout, cin=cin, taps=taps)
-    ref = torch.nn.grad.conv2d_weight(_nchw(x, n_img, cin), (cout, cin, k, k), _nchw(dy, n_img, cout), padding=k // 2)
+    dw = torch.full((cout, cin, k, k), float("nan"), device="cuda")      # overwritten, no zero-fill needed
+    ops.conv_wgrad(dy, x, dw, n_img=n_img, cout=cout, cin=cin, taps=taps, act=act, grad_unscale=1.0 / scale)
+    ref = torch.nn.grad.conv2d_weight(_nchw(xf, n_img, cin), (cout, cin, k, k), _nchw(dyf, n_img, cout), padding=k // 2)
+    ref = ref / scale
     emax, el2 = _errs(dw, ref)
-    print(f"wgrad cout {cout} cin {cin} taps {taps} n_img {n_img}: max {emax:.2e} relL2 {el2:.2e}")
+    print(f"wgrad act {act} cout {cout} cin {cin} taps {taps} n_img {n_img}: max {emax:.2e} relL2 {el2:.2e}")
     assert emax <= 2e-4 and el2 <= 5e-5
-    # a second launch on the same operands gives the same bits (deterministic reduction order)
-    dw2 = torch.zeros_like(dw)
-    ops.conv_wgrad(dy, x, dw2, n_img=n_img, cout=cout, cin=cin, taps=taps)
+    # a second launch on the same operands gives the same bits (turn-ordered split-K reduction)
+    dw2 = torch.empty_like(dw)
+    ops.conv_wgrad(dy, x, dw2, n_img=n_img, cout=cout, cin=cin, taps=taps, act=act, grad_unscale=1.0 / scale)
     assert torch.equal(dw, dw2), "weight gradients differ between two identical launches"
 
 
-CONV_CASES = [(1024, 2240), (1024, 1237), (256, 19)]
+def test_wgrad_flat_fc_embed_shape():
+    """dW of fc_embed_attn (:244): dY (2240 x 128), X (2240 x 133120), both operand types."""
+    from videonavqa_b200 import ops
+    for act in (0, 1):
+        dy, dyf = _rand((2240, 128), 21, scale=0.1, act=act)
+        x, xf = _rand((2240, 133120), 22, relu=True, act=act)
+        dw = torch.empty(128, 133120, device="cuda")
+        ops.conv_wgrad(dy, x, dw, n_img=2240, cout=128, cin=133120, taps=1, flat=True, act=act)
+        emax, el2 = _errs(dw, dyf.t() @ xf)
+        print(f"wgrad flat act {act}: max {emax:.2e} relL2 {el2:.2e}")
+        assert emax <= 2e-4 and el2 <= 5e-5
 
 
+CONV_CASES = [(1024, 2240), (1024, 1237), (256, 19), (96, 5)]
+
+
+def _out_tol(act):
+    """outputs that feed the next MMA are rounded to the operand type: 2^-11 relative either way"""
+    return 1e-3, 5e-4
+
+
+@pytest.mark.parametrize("act", ACTS)
 @pytest.mark.parametrize("C,n_img", CONV_CASES)
-def test_conv3x3_film_epilogue_full_tensor(C, n_img):
-    """conv3x3 + bias -> z ; relu(alpha*z + beta) + res (models/film_attn_pt_stem.py:224-241), CTA-pair kernel."""
+def test_conv3x3_film_epilogue_full_tensor(C, n_img, act):
+    """conv3x3 + bias -> z ; relu(alpha*z + beta) + res (models/film_attn_pt_stem.py:224-241)."""
     from videonavqa_b200 import ops
     from videonavqa_b200._lib import EPI_FILM
-    res = _rand((n_img, 130, C), 3, relu=True)
-    w = _rand((C, C, 3, 3), 4, scale=0.01)
-    bias = _rand((C,), 5, scale=0.1)
+    res, resf = _rand((n_img, 130, C), 3, relu=True, act=act)
+    _, w = _rand((C, C, 3, 3), 4, scale=0.01, act=act)          # fp32 master weights holding operand-exact values
+    _, bias = _rand((C,), 5, scale=0.1)
     n_rows = 7
-    film = _rand((n_rows, 2 * C), 6, relu=True)
+    _, film = _rand((n_rows, 2 * C), 6, relu=True)
     film_row = (torch.arange(n_img, device="cuda", dtype=torch.int32) * 5) % n_rows
     z = torch.empty_like(res)
     out = torch.empty_like(res)
-    ops.conv_gemm(ops.pack_conv_weight(w), res, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_FILM, out=out, bias=bias,
-                  film=film, film_row=film_row, film_ld=film.stride(0), alpha_off=0, res=res, z_out=z)
-    zr = F.conv2d(_nchw(res, n_img, C), w, bias, padding=1).permute(0, 2, 3, 1).reshape(n_img, 130, C)
-    emax, el2 = _errs(z, zr)
-    print(f"conv3x3 z C {C} n_img {n_img}: max {emax:.2e} relL2 {el2:.2e}")
-    assert emax <= 5e-5 and el2 <= 3e-5
+    ops.conv_gemm(ops.pack_conv_weight(w, act=act), res, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_FILM, out=out,
+                  bias=bias, film=film, film_row=film_row, film_ld=film.stride(0), alpha_off=0, res=res, z_out=z, act=act)
+    zr = F.conv2d(_nchw(resf, n_img, C), w, bias, padding=1).permute(0, 2, 3, 1).reshape(n_img, 130, C)
+    emax, el2 = _errs(z.float(), zr)
+    print(f"conv3x3 z act {act} C {C} n_img {n_img}: max {emax:.2e} relL2 {el2:.2e}")
+    if act:
+        assert emax <= 1e-3 and el2 <= 5e-4            # z is stored in fp16
+    else:
+        assert emax <= 5e-5 and el2 <= 3e-5            # z is stored exactly (fp32)
     fr = film[film_row.long()]
-    outr = torch.relu(fr[:, None, :C] * zr + fr[:, None, C:]) + res
-    emax, el2 = _errs(out, outr)            # `out` is additionally rounded to tf32 (it feeds the next MMA)
-    assert emax <= 1e-3 and el2 <= 5e-4
-    assert torch.equal(out, O.tf32_round(out))
+    outr = torch.relu(fr[:, None, :C] * zr + fr[:, None, C:]) + resf
+    emax, el2 = _errs(out.float(), outr)
+    assert emax <= _out_tol(act)[0] and el2 <= _out_tol(act)[1]
+    if not act:
+        assert torch.equal(out, O.tf32_round(out))
 
 
+@pytest.mark.parametrize("act", ACTS)
 @pytest.mark.parametrize("C,n_img", CONV_CASES)
-def test_conv3x3_dgrad_epilogue_full_tensor(C, n_img):
+def test_conv3x3_dgrad_epilogue_full_tensor(C, n_img, act):
     """data gradient of conv3x3 fused with the residual-branch add and the conv1x1 ReLU mask + its bias gradient."""
     from videonavqa_b200 import ops
     from videonavqa_b200._lib import EPI_DGRAD_RES
-    dz = _rand((n_img, 130, C), 7, scale=0.05)
-    dout = _rand((n_img, 130, C), 8, scale=0.05)
-    res = _rand((n_img, 130, C), 9, relu=True)
-    w = _rand((C, C, 3, 3), 10, scale=0.01)
+    scale = 4096.0 if act else 1.0
+    dz, dzf = _rand((n_img, 130, C), 7, scale=0.05, act=act)
+    dout, doutf = _rand((n_img, 130, C), 8, scale=0.05, act=act)
+    res, resf = _rand((n_img, 130, C), 9, relu=True, act=act)
+    _, w = _rand((C, C, 3, 3), 10, scale=0.01, act=act)
     dpre = torch.empty_like(dz)
     db = torch.zeros(C, device="cuda")
-    ops.conv_gemm(ops.pack_conv_weight(w, True), dz, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_DGRAD_RES, out=dpre,
-                  add=dout, res=res, dbias=db)
-    dres = torch.nn.grad.conv2d_input((n_img, C, 10, 13), w, _nchw(dz, n_img, C), padding=1)
-    ref = (dres.permute(0, 2, 3, 1).reshape(n_img, 130, C) + dout) * (res > 0)
-    emax, el2 = _errs(dpre, ref)
-    print(f"dgrad3x3 C {C} n_img {n_img}: max {emax:.2e} relL2 {el2:.2e}")
-    assert emax <= 1e-3 and el2 <= 5e-4      # output rounded to tf32
-    emax, _ = _errs(db, dpre.double().sum((0, 1)).float())
+    ops.conv_gemm(ops.pack_conv_weight(w, True, act), dz, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_DGRAD_RES,
+                  out=dpre, add=dout, res=res, dbias=db, act=act, grad_unscale=1.0 / scale)
+    dres = torch.nn.grad.conv2d_input((n_img, C, 10, 13), w, _nchw(dzf, n_img, C), padding=1)
+    ref = (dres.permute(0, 2, 3, 1).reshape(n_img, 130, C) + doutf) * (resf > 0)
+    emax, el2 = _errs(dpre.float(), ref)
+    print(f"dgrad3x3 act {act} C {C} n_img {n_img}: max {emax:.2e} relL2 {el2:.2e}")
+    assert emax <= _out_tol(act)[0] and el2 <= _out_tol(act)[1]
+    emax, _ = _errs(db, dpre.double().sum((0, 1)).float() / scale)
     assert emax <= 1e-4
 
 
-def test_conv1x1_and_conv_init_full_size():
+@pytest.mark.parametrize("act", ACTS)
+def test_conv1x1_conv_init_and_split_k_full_size(act):
     from videonavqa_b200 import ops
-    from videonavqa_b200._lib import EPI_BIAS_RELU, EPI_BIAS_RELU_AFFINE
+    from videonavqa_b200._lib import EPI_BIAS_RELU, EPI_BIAS_RELU_AFFINE, EPI_BIAS_RELU_STATS, EPI_PARTIAL, EPI_PLAIN
     n_img, C = 2240, 1024
-    x = _rand((n_img, 130, C), 11, relu=True)
-    w1 = _rand((C, C, 1, 1), 12, scale=0.03)
-    b1 = _rand((C,), 13, scale=0.1)
+    x, xf = _rand((n_img, 130, C), 11, relu=True, act=act)
+    _, w1 = _rand((C, C, 1, 1), 12, scale=0.03, act=act)
+    _, b1 = _rand((C,), 13, scale=0.1)
     out = torch.empty_like(x)
-    ops.conv_gemm(ops.pack_conv_weight(w1), x, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_BIAS_RELU, out=out, bias=b1)
-    ref = torch.relu(F.conv2d(_nchw(x, n_img, C), w1, b1)).permute(0, 2, 3, 1).reshape(n_img, 130, C)
-    emax, el2 = _errs(out, ref)
+    ops.conv_gemm(ops.pack_conv_weight(w1, act=act), x, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_BIAS_RELU, out=out,
+                  bias=b1, act=act)
+    ref = torch.relu(F.conv2d(_nchw(xf, n_img, C), w1, b1)).permute(0, 2, 3, 1).reshape(n_img, 130, C)
+    emax, el2 = _errs(out.float(), ref)
     assert emax <= 1e-3 and el2 <= 5e-4
-    x0 = _rand((n_img, 130, 512), 14, relu=True)
-    w0 = _rand((C, 512, 3, 3), 15, scale=0.02)
-    scale = _rand((C,), 16).abs() + 0.5
-    shift = _rand((C,), 17)
-    y = torch.empty(n_img, 130, C, device="cuda")
-    ops.conv_gemm(ops.pack_conv_weight(w0), x0, taps=9, cin=512, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_AFFINE, out=y,
-                  bias=b1, scale=scale, shift=shift)
-    ref = torch.relu(F.conv2d(_nchw(x0, n_img, 512), w0, b1, padding=1)).permute(0, 2, 3, 1).reshape(n_img, 130, C)
-    ref = ref * scale + shift
-    emax, el2 = _errs(y, ref)
+    # 1x1 data gradient (EPI_PLAIN): the kernel that wedged in round 1
+    dx = torch.empty_like(x)
+    ops.conv_gemm(ops.pack_conv_weight(w1, True, act), x, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_PLAIN, out=dx,
+                  act=act)
+    ref = F.conv2d(_nchw(xf, n_img, C), w1.permute(1, 0, 2, 3).contiguous()).permute(0, 2, 3, 1).reshape(n_img, 130, C)
+    emax, el2 = _errs(dx.float(), ref)
+    assert emax <= (1e-3 if act else 5e-5) and el2 <= (5e-4 if act else 3e-5)
+    # conv_init: eval affine and train statistics
+    x0, x0f = _rand((n_img, 130, 512), 14, relu=True, act=act)
+    _, w0 = _rand((C, 512, 3, 3), 15, scale=0.02, act=act)
+    scale = _rand((C,), 16)[1].abs() + 0.5
+    _, shift = _rand((C,), 17)
+    y = torch.empty(n_img, 130, C, device="cuda", dtype=x.dtype)
+    ops.conv_gemm(ops.pack_conv_weight(w0, act=act), x0, taps=9, cin=512, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_AFFINE,
+                  out=y, bias=b1, scale=scale, shift=shift, act=act)
+    pre = torch.relu(F.conv2d(_nchw(x0f, n_img, 512), w0, b1, padding=1)).permute(0, 2, 3, 1).reshape(n_img, 130, C)
+    emax, el2 = _errs(y.float(), pre * scale + shift)
     assert emax <= 1e-3 and el2 <= 5e-4
+    T = 35
+    img_frame = (torch.arange(n_img, device="cuda", dtype=torch.int32) // 64)
+    stat = torch.zeros(2, T, C, device="cuda", dtype=torch.float64)
+    y0 = torch.empty(n_img, 130, C, device="cuda")
+    ops.conv_gemm(ops.pack_conv_weight(w0, act=act), x0, taps=9, cin=512, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_STATS,
+                  out=y0, bias=b1, img_frame=img_frame, stat_sum=stat[0], stat_sq=stat[1], act=act)
+    emax, el2 = _errs(y0, pre)
+    assert emax <= 5e-5 and el2 <= 3e-5                # BatchNorm input stays fp32 for both operand types
+    s_ref = pre.double().view(T, 64 * 130, C).sum(1)
+    assert float((stat[0] - s_ref).abs().max() / s_ref.abs().max()) <= 1e-5
+    # fc_embed_attn: split-K partial GEMM over the flattened map
+    A, K = 128, 130 * C
+    _, wfc = _rand((A, K), 18, scale=0.01, act=act)
+    wq = wfc.half() if act else wfc
+    splits = 10
+    partial = torch.empty(splits, n_img, A, device="cuda")
+    ops.conv_gemm(wq, x.view(n_img, K), taps=1, cin=K // splits, cout=A, n_img=n_img, epi=EPI_PARTIAL, out=partial,
+                  flat=True, x_ld=K, splits=splits, act=act)
+    emax, el2 = _errs(partial.sum(0), xf.view(n_img, K) @ wfc.t())
+    assert emax <= 5e-5 and el2 <= 3e-5

@@ -85,9 +85,14 @@ def test_flat_bucket_training_matches_plain_autograd_path():
         assert p0.grad.data_ptr() == ob.flat.grad_views[0].data_ptr()
         ob.step()
         assert abs(la.item() - lb.item()) <= 2e-4 * abs(la.item()), (step, la.item(), lb.item())
+    # Adam divides by sqrt(v): in the first steps an element's update is ~lr * sign(g), so elements whose gradient is
+    # rounding noise (bias / statistic reductions use atomics) may move in opposite directions - bound the relative L2
+    # tightly and the worst element by 2 * lr * steps
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        err = float((pa.detach() - pb.detach()).abs().max() / pa.detach().abs().max().clamp_min(1e-12))
-        assert err <= 5e-4, (n, err)        # weight-gradient reductions are atomically ordered (not bit-stable)
+        d = (pa.detach() - pb.detach()).double()
+        rel = float(d.norm() / pa.detach().double().norm().clamp_min(1e-12))
+        assert rel <= 2e-3, (n, rel)
+        assert float(d.abs().max()) <= 2 * 1e-3 * 3 + 1e-6, (n, float(d.abs().max()))
     # state_dict still has the reference layout and loads into a fresh module
     sd = mb.state_dict()
     mc = _small_model(3)

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), f"libvnqa_b200.so does not export {s}"
     assert sorted(_lib.SIGNATURES) == syms, set(_lib.SIGNATURES) ^ set(syms)
-    assert handle.vnqa_abi_version() == 1
+    assert handle.vnqa_abi_version() == 2
 
 
 def test_conv_args_struct_matches_header_field_order():
@@ -210,11 +210,12 @@ def test_bench_kernel_summary_helpers():
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    klass = {"conv_gemm.9tap.epi3.k1024.n1024": [62.0, 10, 5.496e12], "hbm.film_bwd": [5.5, 10, 3.578e9],
-             "empty": [0.0, 0, 1.0]}
+    klass = {"conv_gemm.9tap.epi3.k1024.n1024": [62.0, 10, 5.496e12, [6.0] * 5 + [6.4] * 5],
+             "hbm.film_bwd": [5.5, 10, 3.578e9, [0.55] * 10], "empty": [0.0, 0, 1.0, []]}
     k = bench.summarise_kernels(klass, steps=2, ms_per_step=140.0)
     assert abs(k["conv_gemm.9tap.epi3.k1024.n1024"]["tflops"] - 886.5) < 1 and "empty" not in k
     assert abs(k["hbm.film_bwd"]["gb_per_s"] - 6505.5) < 1 and k["hbm.film_bwd"]["launches_per_step"] == 5
+    assert k["conv_gemm.9tap.epi3.k1024.n1024"]["ms_min_med_max"] == [6.0, 6.4, 6.4]
     r = bench.hbm_roofline(k, {"hbm_gbs": 6547.8})
     assert r["bound"] == "hbm" and 0.98 < r["frac"] < 1.0
     assert bench.hbm_roofline({}, {}) is None

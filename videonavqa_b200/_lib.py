@@ -29,11 +29,13 @@ class ConvArgs(ctypes.Structure):
         ("img_frame", c_void_p), ("stat_sum", c_void_p), ("stat_sq", c_void_p),
         ("film", c_void_p), ("film_row", c_void_p), ("film_ld", c_int32), ("alpha_off", c_int32),
         ("res", c_void_p), ("z_out", c_void_p), ("add", c_void_p), ("dbias", c_void_p),
+        ("act_dtype", c_int32), ("out_f32", c_int32), ("grad_unscale", c_float),
     ]
 
 
 EPI_BIAS_RELU, EPI_BIAS_RELU_AFFINE, EPI_BIAS_RELU_STATS, EPI_FILM, EPI_PARTIAL, EPI_DGRAD_RES = 0, 1, 2, 3, 4, 5
 EPI_PLAIN = 7
+ACT_TF32, ACT_FP16 = 0, 1
 
 P, I32, I64, F32 = c_void_p, c_int32, c_int64, c_float
 
@@ -45,18 +47,20 @@ SIGNATURES = {
     "vnqa_sm_count": [],
     "vnqa_debug_install": [P],
     "vnqa_debug_build": [],
-    "vnqa_frames_to_nhwc": [P, P, P, I32, I32, I32, P],
-    "vnqa_pack_conv_weight": [P, P, I32, I32, I32, I32, I32, P],
+    "vnqa_frames_to_nhwc": [P, P, P, I32, I32, I32, I32, P],
+    "vnqa_pack_conv_weight": [P, P, I32, I32, I32, I32, I32, I32, P],
+    "vnqa_to_half": [P, P, I64, F32, P],
     "vnqa_permute_fc_weight": [P, P, I32, I32, I32, I32, P],
     "vnqa_conv_gemm": [POINTER(ConvArgs), P],
-    "vnqa_conv_wgrad": [P, P, P, P, I32, I32, I32, I32, I32, P],
+    "vnqa_conv_wgrad_ws_bytes": [I32, I32, I32, POINTER(c_int64)],
+    "vnqa_conv_wgrad": [P, P, P, P, I32, I32, I32, I32, I32, I32, F32, P],
     "vnqa_sgemm": [P, P, P, P, I32, I32, I32, I64, I64, I64, I64, I64, I32, I32, I32, P],
     "vnqa_colsum": [P, I32, I32, I64, P, I32, P],
     "vnqa_bn_finalize_train": [P, P, P, I32, I32, P, P, P, P, F32, F32, P, P, P, P, P],
     "vnqa_bn_eval_affine": [P, P, P, P, F32, I32, P, P, P],
-    "vnqa_bn_apply": [P, P, P, P, P, I32, I32, P],
-    "vnqa_bn_backward": [P, P, P, P, I32, P, P, P, I32, I32, P, P, P, P, P, P, P],
-    "vnqa_film_backward": [P, P, P, P, I32, I32, I32, I32, P, P, P, I32, P],
+    "vnqa_bn_apply": [P, P, P, P, P, I32, I32, I32, P],
+    "vnqa_bn_backward": [P, P, P, P, I32, P, P, P, I32, I32, P, P, P, P, P, P, I32, F32, P],
+    "vnqa_film_backward": [P, P, P, P, I32, I32, I32, I32, P, P, P, I32, I32, F32, P],
     "vnqa_splitk_reduce": [P, I32, I32, I32, P, P, P, P],
     "vnqa_gather_rows": [P, P, I32, I32, P, I32, P],
     "vnqa_gp_maxpool": [P, P, I32, I32, I32, P, P, P],
@@ -89,7 +93,7 @@ SIGNATURES = {
     "vnqa_attn_tail_forward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "vnqa_attn_tail_backward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
 }
-_RESTYPES = {"vnqa_last_error": c_char_p, "vnqa_nccl_stream": c_void_p}
+_RESTYPES = {"vnqa_last_error": c_char_p, "vnqa_nccl_stream": c_void_p, "vnqa_conv_wgrad_ws_bytes": c_int64}
 
 _lib = None
 
@@ -107,7 +111,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # AttributeError if the library does not export a declared symbol
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, c_int32)
-        if handle.vnqa_abi_version() != 1:
+        if handle.vnqa_abi_version() != 2:
             raise VnqaError("libvnqa_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -28,12 +28,49 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool atom32) {
+namespace {
+struct TmapKey {
+  const void* base;
+  uint64_t dims[4], strides[3];
+  uint32_t box[4];
+  int rank, half, atom32, dev;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+  bool valid = false;
+  TmapKey key;
+  CUtensorMap map;
+};
+constexpr int TMAP_SLOTS = 256;
+TmapSlot g_tmaps[TMAP_SLOTS];
+std::mutex g_tmap_mu;
+}  // namespace
+
+int make_tmap(CUtensorMap* m, const void* base, bool half, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, bool atom32) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return -3;
+  }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.half = half; key.atom32 = atom32;
+  cudaGetDevice(&key.dev);
+  uint64_t h = reinterpret_cast<uint64_t>(base) * 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i > 0) key.strides[i - 1] = strides_bytes[i - 1];
+    h = (h ^ (dims[i] * 0xC2B2AE3D27D4EB4Full + box[i])) * 0x9E3779B97F4A7C15ull;
+  }
+  const int slot = (int)((h >> 40) % TMAP_SLOTS);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmaps[slot].valid && g_tmaps[slot].key == key) {
+      *m = g_tmaps[slot].map;
+      return 0;
+    }
   }
   cuuint64_t gdims[5];
   cuuint64_t gstr[5];
@@ -45,16 +82,19 @@ int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* di
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                   const_cast<void*>(base), gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (atom32 && !half) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu, box %u %u)", (int)r, rank,
-              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, %s, dims %llu %llu, box %u %u)", (int)r, rank,
+              half ? "fp16" : "fp32", (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return -3;
   }
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  g_tmaps[slot].key = key;
+  g_tmaps[slot].map = *m;
+  g_tmaps[slot].valid = true;
   return 0;
 }
 

@@ -34,11 +34,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 
-// fp32 tensor map with 128-byte swizzle (16-byte atoms, or 32-byte atoms for MN-major MMA operands when atom32)
-// and zero out-of-bounds fill. dims/strides innermost first;
-// strides in bytes for dims 1..rank-1.
-int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool atom32 = false);
+// Tiled tensor map (fp32 or fp16 elements) with 128-byte swizzle and zero out-of-bounds fill.  dims / box innermost
+// first; strides in bytes for dims 1..rank-1.  atom32 selects the "128B swizzle, 32B atoms" layout that MN-major
+// fp32/tf32 MMA operands need (16-bit operands use the ordinary 128B swizzle in both majors).  Encoded maps are kept
+// in a small direct-mapped cache keyed by every argument: a training loop presents the same (pointer, shape) pairs
+// step after step (PyTorch's caching allocator returns the same blocks), so cuTensorMapEncodeTiled is rarely re-run.
+int make_tmap(CUtensorMap* m, const void* base, bool half, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, bool atom32 = false);
 
 // host-mapped diagnostics buffer installed by vnqa_debug_install (nullptr unless a debug session set one)
 unsigned long long* debug_buffer();

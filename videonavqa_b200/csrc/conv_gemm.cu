@@ -5,10 +5,16 @@
 //
 //   D[co][pix] = sum_{tap, ci} Wp[tap][co][ci] * X[pix (+) tap][ci]
 //
+// ONE kernel source for both operand types (template T, optype.cuh):
+//   float  - fp32 storage holding tf32-representable values, tcgen05.mma.kind::tf32
+//   __half - fp16 storage (the same 10-bit mantissa), tcgen05.mma.kind::f16: twice the MMA rate, half the bytes
+// A stage row is one 128-byte swizzle row in both cases (32 fp32 or 64 fp16 reduction elements), one MMA consumes
+// 32 bytes of it, so the pipeline - stage bytes, barriers, tile shapes - is identical; fp32 accumulation in TMEM.
+//
 // Orientation: the UMMA M dimension (TMEM lanes) is the OUTPUT CHANNEL, the N dimension (208 TMEM columns) is a
 // block of pixels = 8 frame images x 2 image rows x 13 columns.  130-pixel images do not tile by 128, but
 // 13*16 = 208 is a legal UMMA N, so no MMA work is wasted on padding.  The pixel block of filter tap (dy,dx) is a
-// 4-D TMA box {32 ch, 13 w, 2 h, images} at coordinate {k, dx, h0+dy, n0}; the zero halo of the 3x3 filter is the
+// 4-D TMA box {32|64 ch, 13 w, 2 h, images} at coordinate {k, dx, h0+dy, n0}; the zero halo of the 3x3 filter is the
 // TMA out-of-bounds fill, so activations are stored unpadded.
 //
 // Two variants of the same pipeline (template NCTA):
@@ -23,15 +29,15 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "optype.cuh"
 #include "ptx.cuh"
 
 namespace vnqa {
 
 constexpr int BM = 128;            // output channels per CTA tile (TMEM lanes)
 constexpr int BN = 208;            // pixels per tile (TMEM columns) = 8 * 2 * 13
-constexpr int BK = 32;             // fp32 reduction elements per stage = one 128-byte swizzle row
-constexpr int UMMA_K = 8;          // tf32: 32 bytes per instruction
-constexpr int A_BYTES = BM * BK * 4;           // 16384
+constexpr int ROW_BYTES = 128;     // reduction bytes per stage row = one swizzle row (32 fp32 / 64 fp16)
+constexpr int A_BYTES = BM * ROW_BYTES;        // 16384
 constexpr int ACC_COLS = 256;                  // TMEM column stride between the two accumulator stages
 constexpr int TMEM_COLS = 512;
 constexpr int IMG_PER_TILE = 8;
@@ -41,18 +47,17 @@ constexpr int NUM_THREADS = 256;
 template <int NCTA>
 struct Cfg {
   static constexpr int B_ROWS = BN / NCTA;                 // pixel rows staged per CTA
-  static constexpr int B_BYTES = B_ROWS * BK * 4;          // 26624 / 13312 (multiples of 1024)
+  static constexpr int B_BYTES = B_ROWS * ROW_BYTES;       // 26624 / 13312 (multiples of 1024)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 43008 / 29696
   static constexpr int STAGES = NCTA == 1 ? 5 : 7;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct KParams {
-  int taps, k_chunks, m_tiles, n_tiles, splits, rows_pad, flat, cout, n_img, epi, no_round;
-  int debug_n;  // debug 2 only: override the MMA N (timing experiments)
-  int debug;  // bring-up experiments (VNQA_CONV_DEBUG): 1 skip B loads, 2 skip all loads, 3 skip MMAs; results are garbage
+  int taps, k_chunks, m_tiles, n_tiles, splits, rows_pad, flat, cout, n_img, no_round;
+  int out_f32;                 // fp16 operands only: BIAS_RELU / PLAIN store fp32 (tensors that leave the fp16 domain)
   long long out_split_stride;  // PARTIAL: n_img * cout
-  float* out;
+  void* out;
   const float* bias;
   const float* scale;
   const float* shift;
@@ -62,14 +67,13 @@ struct KParams {
   const float* film;
   const int* film_row;
   int film_ld, alpha_off;
-  const float* res;
-  float* z_out;
-  const float* add;
+  const void* res;
+  void* z_out;
+  const void* add;
   float* dbias;
-  unsigned long long* dbg;   // VNQA_DEBUG_MBAR builds: host-mapped diagnostics buffer (ptx.cuh), else unused
+  float grad_unscale;          // DGRAD_RES: dbias += grad_unscale * column sums (1 unless the signals carry a loss scale)
+  unsigned long long* dbg;     // VNQA_DEBUG_MBAR builds: host-mapped diagnostics buffer (ptx.cuh), else unused
 };
-
-__device__ __forceinline__ float rnd(float x, int no_round) { return no_round ? x : tf32_round(x); }
 
 struct TileCoord {
   int mt, nt, sp;
@@ -89,9 +93,10 @@ __device__ __forceinline__ TileCoord decode_tile(int item, const KParams& p, int
 
 // ------------------------------------------------------------------------------------------------ epilogue
 // One accumulator tile (128 channels x 208 pixels) from TMEM to global memory; thread = output channel.
-template <int EPI>
+template <int EPI, typename T>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord& tc, uint32_t t_base, int ew,
                                               int lane) {
+  using O = Op<T>;
   const int co = tc.mt * BM + ew * 32 + lane;
   const bool co_ok = co < p.cout;
   float bias = 0.f, scale = 1.f, shift = 0.f;
@@ -103,8 +108,11 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord&
     scale = __ldg(p.scale + co);
     shift = __ldg(p.shift + co);
   }
-  float* out = p.out;
-  if (EPI == VNQA_EPI_PARTIAL) out += (long long)tc.sp * p.out_split_stride;
+  // activation-typed (T) and fp32 views of the output; which one is used is a property of the epilogue
+  T* out_t = reinterpret_cast<T*>(p.out);
+  float* out_f = reinterpret_cast<float*>(p.out);
+  if (EPI == VNQA_EPI_PARTIAL) out_f += (long long)tc.sp * p.out_split_stride;
+  const bool f32_out = O::HALF && p.out_f32;    // fp16 path only; the tf32 path stores fp32 through out_t anyway
 
   double st_sum = 0.0, st_sq = 0.0;  // STATS: running per-frame accumulators
   int st_frame = -1;
@@ -131,73 +139,86 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord&
       nvalid = img < p.n_img ? ROWS_PER_IMG_TILE : 0;
     }
     if (nvalid > 0 && co_ok) {
-    float* orow = out + row0 * p.cout + co;
+      const long long o0 = row0 * p.cout + co;
+      const long long ld = p.cout;
 
-    if (EPI == VNQA_EPI_BIAS_RELU) {
+      if (EPI == VNQA_EPI_BIAS_RELU) {
 #pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
-        if (r < nvalid) orow[(long long)r * p.cout] = rnd(fmaxf(__uint_as_float(v[r]) + bias, 0.f), p.no_round);
-    } else if (EPI == VNQA_EPI_BIAS_RELU_AFFINE) {
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) {
+            const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
+            if (f32_out) out_f[o0 + r * ld] = y;
+            else O::st(out_t + o0 + r * ld, y, p.no_round);
+          }
+      } else if (EPI == VNQA_EPI_BIAS_RELU_AFFINE) {
 #pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
-        if (r < nvalid) orow[(long long)r * p.cout] = rnd(fmaf(fmaxf(__uint_as_float(v[r]) + bias, 0.f), scale, shift), p.no_round);
-    } else if (EPI == VNQA_EPI_BIAS_RELU_STATS) {
-      const int fr = __ldg(p.img_frame + img);
-      if (fr != st_frame) {
-        if (st_frame >= 0) {
-          atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
-          atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid)
+            O::st(out_t + o0 + r * ld, fmaf(fmaxf(__uint_as_float(v[r]) + bias, 0.f), scale, shift), p.no_round);
+      } else if (EPI == VNQA_EPI_BIAS_RELU_STATS) {
+        const int fr = __ldg(p.img_frame + img);
+        if (fr != st_frame) {
+          if (st_frame >= 0) {
+            atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
+            atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
+          }
+          st_frame = fr; st_sum = 0.0; st_sq = 0.0;
         }
-        st_frame = fr; st_sum = 0.0; st_sq = 0.0;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
+          out_f[o0 + r * ld] = y;           // BatchNorm input stays fp32 (normalised by bn_apply)
+          s1 += y;
+          s2 = fmaf(y, y, s2);
+        }
+        st_sum += (double)s1;
+        st_sq += (double)s2;
+      } else if (EPI == VNQA_EPI_FILM) {
+        const float* frow = p.film + (long long)__ldg(p.film_row + img) * p.film_ld + p.alpha_off;
+        const float alpha = __ldg(frow + co);
+        const float beta = __ldg(frow + p.cout + co);
+        const T* rrow = reinterpret_cast<const T*>(p.res) + o0;
+        float rv[ROWS_PER_IMG_TILE];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) rv[r] = O::ld(rrow + r * ld);
+        if (p.z_out != nullptr) {
+          T* zrow = reinterpret_cast<T*>(p.z_out) + o0;
+#pragma unroll
+          for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) O::st(zrow + r * ld, __uint_as_float(v[r]) + bias, 1);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          const float z = __uint_as_float(v[r]) + bias;
+          O::st(out_t + o0 + r * ld, fmaxf(fmaf(alpha, z, beta), 0.f) + rv[r], p.no_round);
+        }
+      } else if (EPI == VNQA_EPI_PARTIAL) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) out_f[o0 + r * ld] = __uint_as_float(v[r]);
+      } else if (EPI == VNQA_EPI_PLAIN) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) {
+            if (f32_out) out_f[o0 + r * ld] = __uint_as_float(v[r]);
+            else O::st(out_t + o0 + r * ld, __uint_as_float(v[r]), 1);
+          }
+      } else if (EPI == VNQA_EPI_DGRAD_RES) {
+        const T* arow = reinterpret_cast<const T*>(p.add) + o0;
+        const T* mrow = reinterpret_cast<const T*>(p.res) + o0;
+        float av[ROWS_PER_IMG_TILE], mv[ROWS_PER_IMG_TILE];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          av[r] = O::ld(arow + r * ld);
+          mv[r] = O::ld(mrow + r * ld);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
+          const float g = mv[r] > 0.f ? O::round(__uint_as_float(v[r]) + av[r]) : 0.f;   // feeds the next MMA
+          O::st(out_t + o0 + r * ld, g, 1);
+          db_acc += g;
+        }
       }
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-        const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
-        orow[(long long)r * p.cout] = y;
-        s1 += y;
-        s2 = fmaf(y, y, s2);
-      }
-      st_sum += (double)s1;
-      st_sq += (double)s2;
-    } else if (EPI == VNQA_EPI_FILM) {
-      const float* frow = p.film + (long long)__ldg(p.film_row + img) * p.film_ld + p.alpha_off;
-      const float alpha = __ldg(frow + co);
-      const float beta = __ldg(frow + p.cout + co);
-      const float* rrow = p.res + row0 * p.cout + co;
-      float rv[ROWS_PER_IMG_TILE];
-#pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) rv[r] = __ldg(rrow + (long long)r * p.cout);
-      if (p.z_out != nullptr) {
-        float* zrow = p.z_out + row0 * p.cout + co;
-#pragma unroll
-        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) zrow[(long long)r * p.cout] = __uint_as_float(v[r]) + bias;
-      }
-#pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-        const float z = __uint_as_float(v[r]) + bias;
-        orow[(long long)r * p.cout] = rnd(fmaxf(fmaf(alpha, z, beta), 0.f) + rv[r], p.no_round);
-      }
-    } else if (EPI == VNQA_EPI_PARTIAL || EPI == VNQA_EPI_PLAIN) {
-#pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
-        if (r < nvalid) orow[(long long)r * p.cout] = __uint_as_float(v[r]);
-    } else if (EPI == VNQA_EPI_DGRAD_RES) {
-      const float* arow = p.add + row0 * p.cout + co;
-      const float* mrow = p.res + row0 * p.cout + co;
-      float av[ROWS_PER_IMG_TILE], mv[ROWS_PER_IMG_TILE];
-#pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-        av[r] = __ldg(arow + (long long)r * p.cout);
-        mv[r] = __ldg(mrow + (long long)r * p.cout);
-      }
-#pragma unroll
-      for (int r = 0; r < ROWS_PER_IMG_TILE; ++r) {
-        const float g = mv[r] > 0.f ? tf32_round(__uint_as_float(v[r]) + av[r]) : 0.f;
-        orow[(long long)r * p.cout] = g;
-        db_acc += g;
-      }
-    }
     }  // nvalid && co_ok
     __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
   }
@@ -205,15 +226,16 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord&
     atomicAdd(p.stat_sum + (long long)st_frame * p.cout + co, st_sum);
     atomicAdd(p.stat_sq + (long long)st_frame * p.cout + co, st_sq);
   }
-  if (EPI == VNQA_EPI_DGRAD_RES && p.dbias != nullptr && co_ok) atomicAdd(p.dbias + co, db_acc);
-
+  if (EPI == VNQA_EPI_DGRAD_RES && p.dbias != nullptr && co_ok) atomicAdd(p.dbias + co, db_acc * p.grad_unscale);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int EPI, int NCTA>
+template <int EPI, int NCTA, typename T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
   using C = Cfg<NCTA>;
+  using O = Op<T>;
+  constexpr int BK = O::BK;   // reduction elements per stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -285,12 +307,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (elect_one()) {
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
             uint8_t* sb = sa + A_BYTES;
-            if (NCTA == 1 && p.debug == 1) {
-              mbar_expect_tx(&full_bar[stage], A_BYTES);
-              tma_load_2d(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
-            } else if (NCTA == 1 && p.debug == 2) {
-              mbar_arrive(&full_bar[stage]);
-            } else if (NCTA == 1) {
+            if (NCTA == 1) {
               mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
               tma_load_2d(&tmA, &full_bar[stage], sa, k_base + kc * BK, tap * p.rows_pad + a_row0);
               tma_load_4d(&tmB, &full_bar[stage], sb, k_base + kc * BK, b1 + dx, b2 + dy, b3);
@@ -309,8 +326,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1 && leader) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    const uint32_t idesc = (p.debug == 2 && p.debug_n > 0) ? umma_idesc_tf32(BM * NCTA, p.debug_n, 0, 0)
-                                                          : umma_idesc_tf32(BM * NCTA, BN, 0, 0);
+    constexpr uint32_t idesc = O::idesc(BM * NCTA, BN, 0, 0);
     constexpr uint64_t dbase = umma_desc_base_sw128(16, 1024);
     int stage = 0;
     uint32_t phase = 0;
@@ -328,11 +344,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t adesc = umma_desc(dbase, sa);
           const uint64_t bdesc = umma_desc(dbase, sa + A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
+          for (int k = 0; k < ROW_BYTES / 32; ++k) {
             // advance 32 bytes (>>4 = 2) inside the 128-byte swizzle row
-            if (p.debug == 3) continue;
-            if (NCTA == 1) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            else umma_tf32_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            O::template mma<NCTA>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           if (NCTA == 1) {
             umma_commit(&empty_bar[stage]);                       // frees the smem stage when the MMAs retire
@@ -358,7 +372,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       MBAR_WAIT(&acc_full[as], aphase, 4, ((long long)item << 20));
       tc_fence_after();
       const uint32_t t_base = tmem_base + (uint32_t(ew * 32) << 16) + as * ACC_COLS;
-      epilogue_tile<EPI>(p, tc, t_base, ew, lane);
+      epilogue_tile<EPI, T>(p, tc, t_base, ew, lane);
       // all TMEM reads of this accumulator stage are done -> hand it back to the (leader's) MMA warp
       tc_fence_before();
       __syncwarp();
@@ -383,11 +397,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #endif
 }
 
-template <int EPI, int NCTA>
+template <int EPI, int NCTA, typename T>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int sms, cudaStream_t st) {
-  auto kern = conv_gemm_kernel<EPI, NCTA>;
+  auto kern = conv_gemm_kernel<EPI, NCTA, T>;
   constexpr int smem = Cfg<NCTA>::SMEM_BYTES;
-  VNQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool attr_set[64] = {false};      // per instantiation and device: the attribute is sticky
+  int dev = 0;
+  VNQA_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    VNQA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   const int items = (kp.m_tiles / NCTA) * kp.n_tiles * kp.splits;
   const int groups = sms / NCTA;
   const int grid = (items < groups ? items : groups) * NCTA;
@@ -407,10 +427,107 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams&
   return 0;
 }
 
-template <int EPI>
+template <int EPI, typename T>
 static int launch_any(int ncta, const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int sms,
                       cudaStream_t st) {
-  return ncta == 2 ? launch<EPI, 2>(tmA, tmB, kp, sms, st) : launch<EPI, 1>(tmA, tmB, kp, sms, st);
+  return ncta == 2 ? launch<EPI, 2, T>(tmA, tmB, kp, sms, st) : launch<EPI, 1, T>(tmA, tmB, kp, sms, st);
+}
+
+// bring-up switch VNQA_CONV_NCTA=1 (single-CTA kernels everywhere), read once
+static int forced_ncta() {
+  static const int v = [] { const char* e = getenv("VNQA_CONV_NCTA"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+template <typename T>
+static int conv_gemm_typed(const vnqa_conv_args* a, cudaStream_t st) {
+  using O = Op<T>;
+  constexpr int BK = O::BK;
+  constexpr int ES = O::BYTES;
+  // fp16: a reduction that is not a multiple of 64 is completed by the TMA out-of-bounds zero fill (both operands)
+  VNQA_REQUIRE(a->cin > 0 && (a->cin * ES) % 16 == 0, "vnqa_conv_gemm: cin must be a positive multiple of %d (got %d)",
+               16 / ES, a->cin);
+  const int splits = a->flat ? (a->splits > 0 ? a->splits : 1) : 1;
+  VNQA_REQUIRE(splits == 1 || a->cin % BK == 0, "vnqa_conv_gemm: split-K needs cin per split to be a multiple of %d", BK);
+  VNQA_REQUIRE(O::HALF || a->cin % BK == 0, "vnqa_conv_gemm: cin must be a multiple of %d (got %d)", BK, a->cin);
+  VNQA_REQUIRE(!a->out_f32 || (O::HALF && (a->epi == VNQA_EPI_BIAS_RELU || a->epi == VNQA_EPI_PLAIN)),
+               "vnqa_conv_gemm: out_f32 is available for fp16 operands with BIAS_RELU and PLAIN");
+
+  KParams kp{};
+  kp.taps = a->taps;
+  kp.k_chunks = (a->cin + BK - 1) / BK;
+  kp.m_tiles = a->rows_pad / BM;
+  kp.n_tiles = a->flat ? (a->n_img + BN - 1) / BN : ((a->n_img + IMG_PER_TILE - 1) / IMG_PER_TILE) * 5;
+  kp.splits = splits;
+  kp.rows_pad = a->rows_pad;
+  kp.flat = a->flat;
+  kp.cout = a->cout;
+  kp.n_img = a->n_img;
+  kp.no_round = a->no_round;
+  kp.out_f32 = a->out_f32;
+  kp.out_split_stride = (long long)a->n_img * a->cout;
+  kp.out = a->out; kp.bias = a->bias; kp.scale = a->scale; kp.shift = a->shift;
+  kp.img_frame = a->img_frame; kp.stat_sum = a->stat_sum; kp.stat_sq = a->stat_sq;
+  kp.film = a->film; kp.film_row = a->film_row; kp.film_ld = a->film_ld; kp.alpha_off = a->alpha_off;
+  kp.res = a->res; kp.z_out = a->z_out; kp.add = a->add; kp.dbias = a->dbias;
+  kp.grad_unscale = a->grad_unscale == 0.f ? 1.f : a->grad_unscale;
+  kp.dbg = debug_buffer();
+
+  // CTA pairs (cta_group::2) whenever the output channels split into an even number of 128-row tiles
+  int ncta = (kp.m_tiles % 2 == 0) ? 2 : 1;
+  if (forced_ncta() == 1) ncta = 1;
+
+  // A: packed weights, 2-D {K, rows}
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t ktot = a->flat ? (uint64_t)a->cin * splits : (uint64_t)a->cin;
+    const uint64_t dims[2] = {ktot, (uint64_t)a->taps * a->rows_pad};
+    const uint64_t strides[1] = {ktot * ES};
+    const uint32_t box[2] = {BK, BM};
+    if (make_tmap(&tmA, a->w_packed, O::HALF, 2, dims, strides, box)) return -3;
+  }
+  if (a->flat) {
+    const uint64_t ld = a->x_ld > 0 ? (uint64_t)a->x_ld : (uint64_t)a->cin * splits;
+    VNQA_REQUIRE(ld >= (uint64_t)a->cin * splits && (ld * ES) % 16 == 0, "vnqa_conv_gemm: bad x_ld");
+    const uint64_t dims[4] = {(uint64_t)a->cin * splits, (uint64_t)a->n_img, 1, 1};
+    const uint64_t strides[3] = {ld * ES, ld * ES * (uint64_t)a->n_img, ld * ES * (uint64_t)a->n_img};
+    const uint32_t box[4] = {BK, (uint32_t)(BN / ncta), 1, 1};
+    if (make_tmap(&tmB, a->x, O::HALF, 4, dims, strides, box)) return -3;
+  } else {
+    const uint64_t c = (uint64_t)a->cin;
+    const uint64_t dims[4] = {c, VNQA_IMG_W, VNQA_IMG_H, (uint64_t)a->n_img};
+    const uint64_t strides[3] = {c * ES, c * ES * VNQA_IMG_W, c * ES * VNQA_IMG_PIX};
+    const uint32_t box[4] = {BK, VNQA_IMG_W, 2, (uint32_t)(IMG_PER_TILE / ncta)};
+    if (make_tmap(&tmB, a->x, O::HALF, 4, dims, strides, box)) return -3;
+  }
+
+  int sms = vnqa_sm_count();
+  if (sms <= 0) return -2;
+  switch (a->epi) {
+    case VNQA_EPI_BIAS_RELU:
+      VNQA_REQUIRE(a->bias, "conv_gemm: BIAS_RELU needs bias");
+      return launch_any<VNQA_EPI_BIAS_RELU, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_BIAS_RELU_AFFINE:
+      VNQA_REQUIRE(a->bias && a->scale && a->shift, "conv_gemm: AFFINE needs bias/scale/shift");
+      return launch_any<VNQA_EPI_BIAS_RELU_AFFINE, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_BIAS_RELU_STATS:
+      VNQA_REQUIRE(!a->flat && a->bias && a->img_frame && a->stat_sum && a->stat_sq, "conv_gemm: STATS operands");
+      return launch_any<VNQA_EPI_BIAS_RELU_STATS, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_FILM:
+      VNQA_REQUIRE(!a->flat && a->bias && a->film && a->film_row && a->res, "conv_gemm: FILM operands");
+      return launch_any<VNQA_EPI_FILM, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_PARTIAL:
+      return launch_any<VNQA_EPI_PARTIAL, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_PLAIN:
+      VNQA_REQUIRE(splits == 1, "conv_gemm: PLAIN cannot split K");
+      return launch_any<VNQA_EPI_PLAIN, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_DGRAD_RES:
+      VNQA_REQUIRE(!a->flat && a->add && a->res, "conv_gemm: DGRAD_RES operands");
+      return launch_any<VNQA_EPI_DGRAD_RES, T>(ncta, tmA, tmB, kp, sms, st);
+    default:
+      set_error("vnqa_conv_gemm: unknown epilogue %d", a->epi);
+      return -1;
+  }
 }
 
 }  // namespace vnqa
@@ -420,88 +537,12 @@ using namespace vnqa;
 extern "C" int vnqa_conv_gemm(const vnqa_conv_args* a, void* stream) {
   VNQA_REQUIRE(a != nullptr, "vnqa_conv_gemm: null args");
   VNQA_REQUIRE(a->taps == 1 || a->taps == 9, "vnqa_conv_gemm: taps must be 1 or 9 (got %d)", a->taps);
-  VNQA_REQUIRE(a->cin > 0 && a->cin % BK == 0, "vnqa_conv_gemm: cin must be a positive multiple of %d (got %d)", BK, a->cin);
   VNQA_REQUIRE(a->rows_pad % BM == 0 && a->rows_pad >= a->cout, "vnqa_conv_gemm: rows_pad must be cout rounded up to %d", BM);
   VNQA_REQUIRE(a->n_img > 0, "vnqa_conv_gemm: empty batch");
   VNQA_REQUIRE(a->w_packed && a->x && a->out, "vnqa_conv_gemm: null operand");
-  const int splits = a->flat ? (a->splits > 0 ? a->splits : 1) : 1;
   VNQA_REQUIRE(!(a->flat && a->taps != 1), "vnqa_conv_gemm: flat GEMM has one tap");
-
-  KParams kp{};
-  kp.taps = a->taps;
-  kp.k_chunks = a->cin / BK;
-  kp.m_tiles = a->rows_pad / BM;
-  kp.n_tiles = a->flat ? (a->n_img + BN - 1) / BN : ((a->n_img + IMG_PER_TILE - 1) / IMG_PER_TILE) * 5;
-  kp.splits = splits;
-  kp.rows_pad = a->rows_pad;
-  kp.flat = a->flat;
-  kp.cout = a->cout;
-  kp.n_img = a->n_img;
-  kp.epi = a->epi;
-  kp.no_round = a->no_round;
-  { const char* e = getenv("VNQA_CONV_DEBUG"); kp.debug = e ? atoi(e) : 0; }
-  { const char* e = getenv("VNQA_CONV_DEBUG_N"); kp.debug_n = e ? atoi(e) : 0; }
-  kp.out_split_stride = (long long)a->n_img * a->cout;
-  kp.out = a->out; kp.bias = a->bias; kp.scale = a->scale; kp.shift = a->shift;
-  kp.img_frame = a->img_frame; kp.stat_sum = a->stat_sum; kp.stat_sq = a->stat_sq;
-  kp.film = a->film; kp.film_row = a->film_row; kp.film_ld = a->film_ld; kp.alpha_off = a->alpha_off;
-  kp.res = a->res; kp.z_out = a->z_out; kp.add = a->add; kp.dbias = a->dbias;
-  kp.dbg = debug_buffer();
-
-  // CTA pairs (cta_group::2) whenever the output channels split into an even number of 128-row tiles
-  int ncta = (kp.m_tiles % 2 == 0) ? 2 : 1;
-  if (const char* e = getenv("VNQA_CONV_NCTA")) ncta = (atoi(e) == 1 || kp.m_tiles % 2) ? 1 : 2;   // bring-up switch
-
-  // A: packed weights, 2-D {K, rows}
-  CUtensorMap tmA, tmB;
-  {
-    const uint64_t ktot = a->flat ? (uint64_t)a->cin * splits : (uint64_t)a->cin;
-    const uint64_t dims[2] = {ktot, (uint64_t)a->taps * a->rows_pad};
-    const uint64_t strides[1] = {ktot * 4};
-    const uint32_t box[2] = {BK, BM};
-    if (make_tmap_f32(&tmA, a->w_packed, 2, dims, strides, box)) return -3;
-  }
-  if (a->flat) {
-    const uint64_t ld = a->x_ld > 0 ? (uint64_t)a->x_ld : (uint64_t)a->cin * splits;
-    VNQA_REQUIRE(ld >= (uint64_t)a->cin * splits && ld % 4 == 0, "vnqa_conv_gemm: bad x_ld");
-    const uint64_t dims[4] = {(uint64_t)a->cin * splits, (uint64_t)a->n_img, 1, 1};
-    const uint64_t strides[3] = {ld * 4, ld * 4 * (uint64_t)a->n_img, ld * 4 * (uint64_t)a->n_img};
-    const uint32_t box[4] = {BK, (uint32_t)(BN / ncta), 1, 1};
-    if (make_tmap_f32(&tmB, a->x, 4, dims, strides, box)) return -3;
-  } else {
-    const uint64_t c = (uint64_t)a->cin;
-    const uint64_t dims[4] = {c, VNQA_IMG_W, VNQA_IMG_H, (uint64_t)a->n_img};
-    const uint64_t strides[3] = {c * 4, c * 4 * VNQA_IMG_W, c * 4 * VNQA_IMG_PIX};
-    const uint32_t box[4] = {BK, VNQA_IMG_W, 2, (uint32_t)(IMG_PER_TILE / ncta)};
-    if (make_tmap_f32(&tmB, a->x, 4, dims, strides, box)) return -3;
-  }
-
-  int sms = vnqa_sm_count();
-  if (sms <= 0) return -2;
-  cudaStream_t st = as_stream(stream);
-  switch (a->epi) {
-    case VNQA_EPI_BIAS_RELU:
-      VNQA_REQUIRE(a->bias, "conv_gemm: BIAS_RELU needs bias");
-      return launch_any<VNQA_EPI_BIAS_RELU>(ncta, tmA, tmB, kp, sms, st);
-    case VNQA_EPI_BIAS_RELU_AFFINE:
-      VNQA_REQUIRE(a->bias && a->scale && a->shift, "conv_gemm: AFFINE needs bias/scale/shift");
-      return launch_any<VNQA_EPI_BIAS_RELU_AFFINE>(ncta, tmA, tmB, kp, sms, st);
-    case VNQA_EPI_BIAS_RELU_STATS:
-      VNQA_REQUIRE(!a->flat && a->bias && a->img_frame && a->stat_sum && a->stat_sq, "conv_gemm: STATS operands");
-      return launch_any<VNQA_EPI_BIAS_RELU_STATS>(ncta, tmA, tmB, kp, sms, st);
-    case VNQA_EPI_FILM:
-      VNQA_REQUIRE(!a->flat && a->bias && a->film && a->film_row && a->res, "conv_gemm: FILM operands");
-      return launch_any<VNQA_EPI_FILM>(ncta, tmA, tmB, kp, sms, st);
-    case VNQA_EPI_PARTIAL:
-      return launch_any<VNQA_EPI_PARTIAL>(ncta, tmA, tmB, kp, sms, st);
-    case VNQA_EPI_PLAIN:
-      VNQA_REQUIRE(splits == 1, "conv_gemm: PLAIN cannot split K");
-      return launch_any<VNQA_EPI_PLAIN>(ncta, tmA, tmB, kp, sms, st);
-    case VNQA_EPI_DGRAD_RES:
-      VNQA_REQUIRE(!a->flat && a->add && a->res, "conv_gemm: DGRAD_RES operands");
-      return launch_any<VNQA_EPI_DGRAD_RES>(ncta, tmA, tmB, kp, sms, st);
-    default:
-      set_error("vnqa_conv_gemm: unknown epilogue %d", a->epi);
-      return -1;
-  }
+  VNQA_REQUIRE(a->act_dtype == VNQA_ACT_TF32 || a->act_dtype == VNQA_ACT_FP16, "vnqa_conv_gemm: unknown act_dtype %d",
+               a->act_dtype);
+  return a->act_dtype == VNQA_ACT_FP16 ? conv_gemm_typed<__half>(a, as_stream(stream))
+                                       : conv_gemm_typed<float>(a, as_stream(stream));
 }

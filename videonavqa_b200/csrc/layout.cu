@@ -1,5 +1,6 @@
 // K0 and weight-layout kernels (HBM-bound data movement).
 #include "common.h"
+#include "stream_f16.h"
 #include "ptx.cuh"
 
 namespace vnqa {
@@ -71,9 +72,11 @@ __global__ void permute_fc_weight_kernel(const float* __restrict__ w, float* __r
 
 using namespace vnqa;
 
-extern "C" int vnqa_frames_to_nhwc(const float* v_input, float* x_out, const int32_t* img_of, int32_t B, int32_t C,
-                                   int32_t T, void* stream) {
-  VNQA_REQUIRE(v_input && x_out && img_of, "vnqa_frames_to_nhwc: null pointer");
+extern "C" int vnqa_frames_to_nhwc(const float* v_input, void* x_out_, const int32_t* img_of, int32_t B, int32_t C,
+                                   int32_t T, int32_t act_dtype, void* stream) {
+  VNQA_REQUIRE(v_input && x_out_ && img_of, "vnqa_frames_to_nhwc: null pointer");
+  if (act_dtype == VNQA_ACT_FP16) return frames_to_nhwc_h(v_input, x_out_, img_of, B, C, T, as_stream(stream));
+  float* x_out = static_cast<float*>(x_out_);
   VNQA_REQUIRE(C % 32 == 0 && C > 0, "vnqa_frames_to_nhwc: C must be a multiple of 32 (got %d)", C);
   VNQA_REQUIRE(T > 0 && T <= 64 && B > 0 && B <= 65535, "vnqa_frames_to_nhwc: bad B/T (%d, %d)", B, T);
   dim3 grid(VNQA_IMG_PIX, C / 32, B);
@@ -82,11 +85,14 @@ extern "C" int vnqa_frames_to_nhwc(const float* v_input, float* x_out, const int
   return 0;
 }
 
-extern "C" int vnqa_pack_conv_weight(const float* w, float* packed, int32_t cout, int32_t cin, int32_t taps,
-                                     int32_t rows_pad, int32_t transpose_flip, void* stream) {
-  VNQA_REQUIRE(w && packed, "vnqa_pack_conv_weight: null pointer");
+extern "C" int vnqa_pack_conv_weight(const float* w, void* packed_, int32_t cout, int32_t cin, int32_t taps,
+                                     int32_t rows_pad, int32_t transpose_flip, int32_t act_dtype, void* stream) {
+  VNQA_REQUIRE(w && packed_, "vnqa_pack_conv_weight: null pointer");
   VNQA_REQUIRE(taps == 1 || taps == 9, "vnqa_pack_conv_weight: taps must be 1 or 9");
   VNQA_REQUIRE(rows_pad >= (transpose_flip ? cin : cout), "vnqa_pack_conv_weight: rows_pad too small");
+  if (act_dtype == VNQA_ACT_FP16)
+    return pack_conv_weight_h(w, packed_, cout, cin, taps, rows_pad, transpose_flip, as_stream(stream));
+  float* packed = static_cast<float*>(packed_);
   const long long total = (long long)taps * rows_pad * (transpose_flip ? cout : cin);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   pack_conv_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, packed, cout, cin, taps, rows_pad, transpose_flip);

@@ -2,6 +2,7 @@
 // classifier linears are tiny and stay exact), BatchNorm statistics/affine/backward, element-wise FiLM backward,
 // split-K reduction, global max pooling.
 #include "common.h"
+#include "stream_f16.h"
 #include "ptx.cuh"
 
 namespace vnqa {
@@ -395,8 +396,10 @@ extern "C" int vnqa_bn_eval_affine(const float* gamma, const float* beta, const 
   return 0;
 }
 
-extern "C" int vnqa_bn_apply(const float* y, float* x, const int32_t* img_frame, const float* scale, const float* shift,
-                             int32_t n_img, int32_t C, void* stream) {
+extern "C" int vnqa_bn_apply(const float* y, void* x_, const int32_t* img_frame, const float* scale, const float* shift,
+                             int32_t n_img, int32_t C, int32_t act_dtype, void* stream) {
+  if (act_dtype == VNQA_ACT_FP16) return bn_apply_h(y, x_, img_frame, scale, shift, n_img, C, as_stream(stream));
+  float* x = static_cast<float*>(x_);
   VNQA_REQUIRE(C % 4 == 0, "vnqa_bn_apply: C must be a multiple of 4");
   const long long n_vec = (long long)n_img * VNQA_IMG_PIX * C / 4;
   const int blocks = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
@@ -406,12 +409,17 @@ extern "C" int vnqa_bn_apply(const float* y, float* x, const int32_t* img_frame,
   return 0;
 }
 
-extern "C" int vnqa_bn_backward(const float* dx, const float* y, const int32_t* img_frame, const int32_t* frame_ct,
+extern "C" int vnqa_bn_backward(const void* dx_, const float* y, const int32_t* img_frame, const int32_t* frame_ct,
                                 int32_t n_frames, const float* mean, const float* rstd, const float* gamma,
-                                int32_t n_img, int32_t C, float* s1, float* s2, float* dy, float* dbias, float* dgamma,
-                                float* dbeta, void* stream) {
-  VNQA_REQUIRE(dx && y && s1 && s2 && dy && dbias && dgamma && dbeta, "vnqa_bn_backward: null");
+                                int32_t n_img, int32_t C, float* s1, float* s2, void* dy_, float* dbias, float* dgamma,
+                                float* dbeta, int32_t act_dtype, float grad_unscale, void* stream) {
+  VNQA_REQUIRE(dx_ && y && s1 && s2 && dy_ && dbias && dgamma && dbeta, "vnqa_bn_backward: null");
   cudaStream_t st = as_stream(stream);
+  if (act_dtype == VNQA_ACT_FP16)
+    return bn_backward_h(dx_, y, img_frame, frame_ct, n_frames, mean, rstd, gamma, n_img, C, s1, s2, dy_, dbias, dgamma,
+                         dbeta, grad_unscale == 0.f ? 1.f : grad_unscale, st);
+  const float* dx = static_cast<const float*>(dx_);
+  float* dy = static_cast<float*>(dy_);
   VNQA_CHECK_CUDA(cudaMemsetAsync(s1, 0, (size_t)n_frames * C * 4, st));
   VNQA_CHECK_CUDA(cudaMemsetAsync(s2, 0, (size_t)n_frames * C * 4, st));
   dim3 grid((C + 127) / 128, n_img);
@@ -422,10 +430,16 @@ extern "C" int vnqa_bn_backward(const float* dx, const float* y, const int32_t* 
   return 0;
 }
 
-extern "C" int vnqa_film_backward(const float* dout, const float* z, const float* film, const int32_t* film_row,
-                                  int32_t film_ld, int32_t alpha_off, int32_t n_img, int32_t C, float* dz, float* dfilm,
-                                  float* dbias, int32_t mask_relu, void* stream) {
-  VNQA_REQUIRE(dout && z && film && film_row && dz && dfilm && dbias, "vnqa_film_backward: null");
+extern "C" int vnqa_film_backward(const void* dout_, const void* z_, const float* film, const int32_t* film_row,
+                                  int32_t film_ld, int32_t alpha_off, int32_t n_img, int32_t C, void* dz_, float* dfilm,
+                                  float* dbias, int32_t mask_relu, int32_t act_dtype, float grad_unscale, void* stream) {
+  VNQA_REQUIRE(dout_ && z_ && film && film_row && dz_ && dfilm && dbias, "vnqa_film_backward: null");
+  if (act_dtype == VNQA_ACT_FP16)
+    return film_backward_h(dout_, z_, film, film_row, film_ld, alpha_off, n_img, C, dz_, dfilm, dbias, mask_relu,
+                           grad_unscale == 0.f ? 1.f : grad_unscale, as_stream(stream));
+  const float* dout = static_cast<const float*>(dout_);
+  const float* z = static_cast<const float*>(z_);
+  float* dz = static_cast<float*>(dz_);
   VNQA_REQUIRE(C % 4 == 0 && film_ld % 4 == 0 && alpha_off % 4 == 0, "vnqa_film_backward: C/film_ld/alpha_off must be multiples of 4");
   const int threads = C / 4 >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
   film_bwd_kernel<<<n_img, threads, 0, as_stream(stream)>>>(dout, z, film, film_row, film_ld, alpha_off, C, dz, dfilm,

@@ -25,6 +25,32 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+class Precision:
+    """Operand / trunk-activation storage of the tensor-core kernels (include/vnqa_b200.h VNQA_ACT_*).
+
+    ``tf32``: fp32 storage holding tf32-representable values (kind::tf32 MMA).
+    ``fp16``: half storage - the same 10-bit mantissa - for the NHWC input, the BatchNorm output, every ResBlock tensor
+    and the saved pre-FiLM activation (kind::f16 MMA: twice the rate, half the bytes).  BatchNorm input and statistics,
+    FiLM parameters, split-K partials, both LSTMs, the attention tail and every parameter gradient stay fp32.  Backward
+    signals inside the trunk are stored multiplied by ``loss_scale`` (a power of two; they reach 1e-7): d feats is
+    scaled when it is converted to fp16, every kernel that leaves the fp16 domain multiplies by 1 / loss_scale."""
+
+    def __init__(self, operands="tf32", loss_scale=4096.0):
+        if operands not in ("tf32", "fp16"):
+            raise ValueError(f"operands must be 'tf32' or 'fp16' (got {operands!r})")
+        self.name = operands
+        self.fp16 = operands == "fp16"
+        self.act = 1 if self.fp16 else 0
+        self.dtype = torch.float16 if self.fp16 else torch.float32
+        self.loss_scale = float(loss_scale) if self.fp16 else 1.0
+        self.unscale = 1.0 / self.loss_scale
+        self.bk = 64 if self.fp16 else 32           # reduction elements per MMA stage row
+        self.key = "h." if self.fp16 else ""        # prefix of the packed-weight cache keys
+
+
+TF32 = Precision("tf32")
+
+
 class Plan:
     """Ragged-batch bookkeeping (models/film_attn_pt_stem.py:190-210, 245-251) computed once per forward on the
     host from v_lens (ONE device->host read instead of the reference's >= 35)."""
@@ -136,13 +162,15 @@ class WeightCache:
             self._gen[t.data_ptr()] = self._gen.get(t.data_ptr(), 0) + 1
 
 
-def _choose_splits(n_img, k_total):
-    """split-K factor for the fc_embed_attn GEMM: smallest divisor of 130 that fills the SMs."""
+def _choose_splits(n_img, k_total, bk=32):
+    """split-K factor for the fc_embed_attn GEMM: smallest divisor of 130 that fills the SMs (K per split must be a
+    multiple of the MMA stage depth); falls back to the largest legal one."""
     n_tiles = (n_img + 207) // 208
-    for s in (1, 2, 5, 10, 13, 26, 65, 130):
-        if (k_total // s) % 32 == 0 and n_tiles * s >= 140:
+    legal = [s for s in (1, 2, 5, 10, 13, 26, 65, 130) if k_total % s == 0 and (k_total // s) % bk == 0]
+    for s in legal:
+        if n_tiles * s >= 140:
             return s
-    return 130
+    return legal[-1]
 
 
 # ======================================================================================== trunk forward
@@ -175,7 +203,7 @@ def lstm_generator_backward(P, cache, ctx, dfilm, q_input, q_lens32, sink):
 
 
 def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save,
-                  gen_fwd=lstm_generator_forward):
+                  gen_fwd=lstm_generator_forward, prec=TF32):
     """conv_init+ReLU+BN, question encoder + FiLM generator, FiLM ResBlocks.  Returns (x_last, ctx)."""
     dev = v_input.device
     B, c_in = v_input.shape[0], v_input.shape[1]
@@ -184,10 +212,11 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
     while f"film_pipeline.{nb}.weight" in P:
         nb += 1
     n_img = plan.n_img
-    ctx = {"plan": plan, "C": C, "nb": nb, "c_in": c_in}
+    ctx = {"plan": plan, "C": C, "nb": nb, "c_in": c_in, "prec": prec}
+    act, pk = prec.act, prec.key
 
     # K0: frame-image-major NHWC
-    x0 = ops.frames_to_nhwc(v_input, plan.img_of, n_img)
+    x0 = ops.frames_to_nhwc(v_input, plan.img_of, n_img, act)
 
     # ---- question encoder on a side stream (independent of the video until the first FiLM epilogue)
     main = torch.cuda.current_stream()
@@ -203,38 +232,39 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
     film_ready.record(side)
 
     # ---- conv_init -> ReLU -> BatchNorm (:211)
-    w_init = cache.get("conv_init", P["conv_init.weight"], ops.pack_conv_weight)
+    pack = lambda w: ops.pack_conv_weight(w, act=act)     # noqa: E731
+    w_init = cache.get(pk + "conv_init", P["conv_init.weight"], pack)
     if training:
         y0 = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=torch.float32)
         stat = torch.zeros(2, plan.n_frames, C, device=dev, dtype=torch.float64)
-        ops.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_STATS, out=y0,
+        ops.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_STATS, out=y0, act=act,
                       bias=P["conv_init.bias"], img_frame=plan.img_frame, stat_sum=stat[0], stat_sq=stat[1])
         scale, shift, mean, rstd = ops.bn_finalize_train(stat[0], stat[1], plan.frame_ct, plan.n_frames,
                                                          P["bn_init.weight"], P["bn_init.bias"], bn["running_mean"],
                                                          bn["running_var"], BN_MOMENTUM, BN_EPS)
         bn["num_batches_tracked"] += plan.n_frames
-        x = ops.bn_apply(y0, plan.img_frame, scale, shift)
+        x = ops.bn_apply(y0, plan.img_frame, scale, shift, act)
         ctx.update(y0=y0, mean=mean, rstd=rstd)
     else:
         scale, shift = ops.bn_eval_affine(P["bn_init.weight"], P["bn_init.bias"], bn["running_mean"],
                                           bn["running_var"], BN_EPS)
-        x = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=torch.float32)
-        ops.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_AFFINE, out=x,
+        x = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=prec.dtype)
+        ops.conv_gemm(w_init, x0, taps=9, cin=c_in, cout=C, n_img=n_img, epi=EPI_BIAS_RELU_AFFINE, out=x, act=act,
                       bias=P["conv_init.bias"], scale=scale, shift=shift)
 
     # ---- FiLM ResBlocks (:217-241)
     xs, ress, zs = [x], [], []
     for k in range(nb):
-        w1 = cache.get(f"c1x1.{k}", P[f"conv1x1_layers.{k}.weight"], ops.pack_conv_weight)
-        w3 = cache.get(f"c3x3.{k}", P[f"film_pipeline.{k}.weight"], ops.pack_conv_weight)
+        w1 = cache.get(f"{pk}c1x1.{k}", P[f"conv1x1_layers.{k}.weight"], pack)
+        w3 = cache.get(f"{pk}c3x3.{k}", P[f"film_pipeline.{k}.weight"], pack)
         res = torch.empty_like(x)
-        ops.conv_gemm(w1, x, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_BIAS_RELU, out=res,
+        ops.conv_gemm(w1, x, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_BIAS_RELU, out=res, act=act,
                       bias=P[f"conv1x1_layers.{k}.bias"])
         if k == 0:
             main.wait_event(film_ready)
         z = torch.empty_like(x) if save else None
         out = torch.empty_like(x)
-        ops.conv_gemm(w3, res, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_FILM, out=out,
+        ops.conv_gemm(w3, res, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_FILM, out=out, act=act,
                       bias=P[f"film_pipeline.{k}.bias"], film=film, film_row=plan.film_row, film_ld=film.stride(0),
                       alpha_off=2 * k * C, res=res, z_out=z)
         x = out
@@ -265,6 +295,8 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
     """Backward of trunk_forward given d(loss)/d(x_last); fills `grads` (name -> tensor).  mask_relu: the FiLM
     generator ends in a ReLU (attention / global-pooling models)."""
     plan, C, nb, c_in = ctx["plan"], ctx["C"], ctx["nb"], ctx["c_in"]
+    prec = ctx["prec"]
+    act, pk, un = prec.act, prec.key, prec.unscale      # dx_last and every trunk signal carry prec.loss_scale
     n_img, B = plan.n_img, plan.B
     dev = dx_last.device
     film = ctx["film"]
@@ -293,26 +325,27 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
     for k in reversed(range(nb)):
         res, z, x_in = ctx["ress"][k], ctx["zs"][k], ctx["xs"][k]
         db3 = grads.buffer(f"film_pipeline.{k}.bias", P[f"film_pipeline.{k}.bias"])
-        dz = ops.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3, mask_relu=mask_relu)
+        dz = ops.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3, mask_relu=mask_relu, act=act,
+                               grad_unscale=un)
         if k == 0:
             generator_backward()
         grads[f"film_pipeline.{k}.bias"] = db3
         dw3 = grads.buffer(f"film_pipeline.{k}.weight", P[f"film_pipeline.{k}.weight"])
-        ops.conv_wgrad(dz, res, dw3, n_img=n_img, cout=C, cin=C, taps=9)
+        ops.conv_wgrad(dz, res, dw3, n_img=n_img, cout=C, cin=C, taps=9, act=act, grad_unscale=un)
         grads[f"film_pipeline.{k}.weight"] = dw3
-        w3t = cache.get(f"c3x3t.{k}", P[f"film_pipeline.{k}.weight"], lambda w: ops.pack_conv_weight(w, True))
+        w3t = cache.get(f"{pk}c3x3t.{k}", P[f"film_pipeline.{k}.weight"], lambda w: ops.pack_conv_weight(w, True, act))
         db1 = grads.buffer(f"conv1x1_layers.{k}.bias", P[f"conv1x1_layers.{k}.bias"])
         dpre = torch.empty_like(res)
         ops.conv_gemm(w3t, dz, taps=9, cin=C, cout=C, n_img=n_img, epi=EPI_DGRAD_RES, out=dpre, add=dout, res=res,
-                      dbias=db1)
+                      dbias=db1, act=act, grad_unscale=un)
         del dz
         grads[f"conv1x1_layers.{k}.bias"] = db1
         dw1 = grads.buffer(f"conv1x1_layers.{k}.weight", P[f"conv1x1_layers.{k}.weight"])
-        ops.conv_wgrad(dpre, x_in, dw1, n_img=n_img, cout=C, cin=C, taps=1)
+        ops.conv_wgrad(dpre, x_in, dw1, n_img=n_img, cout=C, cin=C, taps=1, act=act, grad_unscale=un)
         grads[f"conv1x1_layers.{k}.weight"] = dw1
-        w1t = cache.get(f"c1x1t.{k}", P[f"conv1x1_layers.{k}.weight"], lambda w: ops.pack_conv_weight(w, True))
+        w1t = cache.get(f"{pk}c1x1t.{k}", P[f"conv1x1_layers.{k}.weight"], lambda w: ops.pack_conv_weight(w, True, act))
         dx = torch.empty_like(res)
-        ops.conv_gemm(w1t, dpre, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_PLAIN, out=dx)
+        ops.conv_gemm(w1t, dpre, taps=1, cin=C, cout=C, n_img=n_img, epi=EPI_PLAIN, out=dx, act=act)
         del dpre
         dout = dx
     # ---- BatchNorm + ReLU + conv_init
@@ -320,12 +353,12 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
     dgamma = grads.buffer("bn_init.weight", P["bn_init.weight"])
     dbeta = grads.buffer("bn_init.bias", P["bn_init.bias"])
     dy0 = ops.bn_backward(dout, ctx["y0"], plan.img_frame, plan.frame_ct, plan.n_frames, ctx["mean"], ctx["rstd"],
-                          P["bn_init.weight"], db0, dgamma, dbeta)
+                          P["bn_init.weight"], db0, dgamma, dbeta, act=act, grad_unscale=un)
     grads["conv_init.bias"] = db0
     grads["bn_init.weight"] = dgamma
     grads["bn_init.bias"] = dbeta
     dw0 = grads.buffer("conv_init.weight", P["conv_init.weight"])
-    ops.conv_wgrad(dy0, ctx["x0"], dw0, n_img=n_img, cout=C, cin=c_in, taps=9)
+    ops.conv_wgrad(dy0, ctx["x0"], dw0, n_img=n_img, cout=C, cin=c_in, taps=9, act=act, grad_unscale=un)
     grads["conv_init.weight"] = dw0
     # ---- join the side stream; its gradients are published (and all-reduced, if a hook is set) from the main stream
     main.wait_event(gen_done[0])
@@ -359,22 +392,22 @@ def question_backward(P, ctx, dh_pass, q_input, q_lens32, grads, enc, dh_steps=N
 
 
 # ======================================================================================== attention model
-def attn_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, T, training, save):
+def attn_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, T, training, save, prec=TF32):
     """FiLMAttnPretrainedStem.forward (models/film_attn_pt_stem.py:188-301)."""
     dev = v_input.device
     B = v_input.shape[0]
     plan = get_plan(v_lens_host, B, T, dev)
-    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save, prec=prec)
     C, n_img = ctx["C"], plan.n_img
     A = P["fc_attn_1.weight"].shape[1]
     # fc_embed_attn over the NHWC-flattened map (:244): split-K tensor-core GEMM + reduction that scatters each
     # frame image to its (clip, frame) row of the zero-padded feature matrix (:245-256)
-    wfc = cache.get("fc_embed", P["fc_embed_attn.weight"], lambda w: ops.permute_fc_weight(w, C))
+    wfc = cache.get(prec.key + "fc_embed", P["fc_embed_attn.weight"], lambda w: _fc_operand(w, C, prec))
     K = IMG_PIX * C
-    splits = _choose_splits(n_img, K)
+    splits = _choose_splits(n_img, K, prec.bk)
     partial = torch.empty(splits, n_img, A, device=dev, dtype=torch.float32)
     ops.conv_gemm(wfc, x, taps=1, cin=K // splits, cout=A, n_img=n_img, epi=EPI_PARTIAL, out=partial, flat=True,
-                  x_ld=K, splits=splits)
+                  x_ld=K, splits=splits, act=prec.act)
     feats = torch.zeros(B, T, A, device=dev, dtype=torch.float32)
     ops.splitk_reduce(partial, splits, n_img, A, P["fc_embed_attn.bias"], plan.feat_row, feats)
     wih_t = cache.get("tail_wih_t", P["lstm_attn.weight_ih"], lambda w: w.t().contiguous())
@@ -388,8 +421,15 @@ def attn_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, 
     return logits, ctx
 
 
+def _fc_operand(w, C, prec):
+    """fc_embed_attn weight (A, C*130) permuted to the NHWC column order, in the operand type."""
+    wp = ops.permute_fc_weight(w, C)
+    return ops.to_half(wp) if prec.fp16 else wp
+
+
 def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None, grad_bucket=None):
     plan, C, A, T = ctx["plan"], ctx["C"], ctx["A"], ctx["T"]
+    prec = ctx["prec"]
     B, n_img = plan.B, plan.n_img
     dev = dlogits.device
     grads = GradSink(grad_hook, grad_bucket)
@@ -418,30 +458,33 @@ def attn_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None, gra
     grads["lstm_attn.bias_ih"] = bsum
     grads["lstm_attn.bias_hh"] = buf("lstm_attn.bias_hh").copy_(bsum)
     # fc_embed_attn backward on the valid (clip, frame) rows
-    df_rows = ops.gather_rows(dfeats.view(B * T, A), plan.feat_row, n_img, A, round_tf32=True)
+    df_rows = ops.gather_rows(dfeats.view(B * T, A), plan.feat_row, n_img, A, round_tf32=not prec.fp16)
     grads["fc_embed_attn.bias"] = ops.colsum(df_rows, out=buf("fc_embed_attn.bias"))
+    if prec.fp16:
+        df_rows = ops.to_half(df_rows, prec.loss_scale)      # d feats enters the fp16 domain scaled
     K = IMG_PIX * C
     x_last = ctx["x_last"].view(n_img, K)
-    dwp = torch.zeros(A, K, device=dev, dtype=torch.float32)
-    ops.conv_wgrad(df_rows, x_last, dwp, n_img=n_img, cout=A, cin=K, taps=1, flat=True)
+    dwp = torch.empty(A, K, device=dev, dtype=torch.float32)
+    ops.conv_wgrad(df_rows, x_last, dwp, n_img=n_img, cout=A, cin=K, taps=1, flat=True, act=prec.act,
+                   grad_unscale=prec.unscale)
     grads["fc_embed_attn.weight"] = ops.permute_fc_weight(dwp, C, inverse=True, out=buf("fc_embed_attn.weight"))
-    wfc = cache.get("fc_embed", P["fc_embed_attn.weight"], lambda w: ops.permute_fc_weight(w, C))
-    wfc_t = cache.get("fc_embed_t", P["fc_embed_attn.weight"],
-                      lambda w: ops.pack_matrix(ops.permute_fc_weight(w, C, n_pad=w.shape[0]), transpose=True))
-    del wfc
-    dx_last = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=torch.float32)
-    ops.conv_gemm(wfc_t, df_rows, taps=1, cin=A, cout=K, n_img=n_img, epi=EPI_PLAIN, out=dx_last, flat=True, x_ld=A)
+    wfc_t = cache.get(prec.key + "fc_embed_t", P["fc_embed_attn.weight"],
+                      lambda w: ops.pack_matrix(ops.permute_fc_weight(w, C, n_pad=w.shape[0]), transpose=True,
+                                                act=prec.act))
+    dx_last = torch.empty(n_img, IMG_PIX, C, device=dev, dtype=prec.dtype)
+    ops.conv_gemm(wfc_t, df_rows, taps=1, cin=A, cout=K, n_img=n_img, epi=EPI_PLAIN, out=dx_last, flat=True, x_ld=A,
+                  act=prec.act)
     trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
     return grads
 
 
 # ======================================================================================== global-pooling model
-def gp_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, training, save):
+def gp_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens32, film_h, film_c, training, save, prec=TF32):
     """FiLMGlobalPoolingPretrainedStem.forward (models/film_global_pooling_pt_stem.py:180-238)."""
     dev = v_input.device
     B, T = v_input.shape[0], v_input.shape[-1]
     plan = get_plan(v_lens_host, B, T, dev)
-    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save)
+    x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save, prec=prec)
     return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
 
 
@@ -450,10 +493,11 @@ def _gp_tail_forward(P, cache, plan, x, ctx, B, T, save):
     dev = x.device
     C, n_img = ctx["C"], plan.n_img
     tail = P["c1x1_tail.weight"].shape[0]
-    wt = cache.get("c1x1_tail", P["c1x1_tail.weight"], ops.pack_conv_weight)
-    y = torch.empty(n_img, IMG_PIX, tail, device=dev, dtype=torch.float32)
+    prec = ctx["prec"]
+    wt = cache.get(prec.key + "c1x1_tail", P["c1x1_tail.weight"], lambda w: ops.pack_conv_weight(w, act=prec.act))
+    y = torch.empty(n_img, IMG_PIX, tail, device=dev, dtype=torch.float32)     # the tail map leaves the MMA domain: fp32
     ops.conv_gemm(wt, x, taps=1, cin=C, cout=tail, n_img=n_img, epi=EPI_BIAS_RELU, out=y, bias=P["c1x1_tail.bias"],
-                  no_round=True)
+                  no_round=True, act=prec.act, out_f32=prec.fp16)
     pooled, arg = ops.gp_maxpool(y, plan.img_of, B, T, tail)
     logits = ops.linear(pooled, P["out_linear.weight"], P["out_linear.bias"])
     if save:
@@ -463,12 +507,12 @@ def _gp_tail_forward(P, cache, plan, x, ctx, B, T, save):
 
 def gp_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None, grad_bucket=None):
     grads = GradSink(grad_hook, grad_bucket)
-    dx_last = _gp_tail_backward(P, ctx, dlogits, grads)
+    dx_last = _gp_tail_backward(P, cache, ctx, dlogits, grads)
     trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads)
     return grads
 
 
-def _gp_tail_backward(P, ctx, dlogits, grads):
+def _gp_tail_backward(P, cache, ctx, dlogits, grads):
     plan, C, tail = ctx["plan"], ctx["C"], ctx["tail"]
     B, n_img = plan.B, plan.n_img
     dlogits = dlogits.contiguous()
@@ -480,11 +524,21 @@ def _gp_tail_backward(P, ctx, dlogits, grads):
     dy2 = dy.view(n_img * IMG_PIX, tail)
     grads["c1x1_tail.bias"] = ops.colsum(dy2, out=grads.buffer("c1x1_tail.bias", P["c1x1_tail.bias"]))
     x_last = ctx["x_last"]
-    # tail conv gradients: tail is tiny (<= 64 channels) -> fp32 SGEMMs
+    prec = ctx["prec"]
     dwt = grads.buffer("c1x1_tail.weight", P["c1x1_tail.weight"])
-    ops.linear_wgrad(dy2, x_last.view(n_img * IMG_PIX, C), ksplit=32, out=dwt.view(tail, C))
+    if not prec.fp16:
+        # tail conv gradients: tail is tiny (<= 64 channels) -> fp32 SGEMMs
+        ops.linear_wgrad(dy2, x_last.view(n_img * IMG_PIX, C), ksplit=32, out=dwt.view(tail, C))
+        grads["c1x1_tail.weight"] = dwt
+        return ops.linear_dgrad(dy2, P["c1x1_tail.weight"].view(tail, C)).view(n_img, IMG_PIX, C)
+    # fp16 trunk: x_last is half, so the tail gradients run on the tensor cores; dy enters the fp16 domain scaled
+    dy_h = ops.to_half(dy, prec.loss_scale)
+    ops.conv_wgrad(dy_h, x_last, dwt, n_img=n_img, cout=tail, cin=C, taps=1, act=1, grad_unscale=prec.unscale)
     grads["c1x1_tail.weight"] = dwt
-    return ops.linear_dgrad(dy2, P["c1x1_tail.weight"].view(tail, C)).view(n_img, IMG_PIX, C)
+    wtt = cache.get("h.c1x1_tail_t", P["c1x1_tail.weight"], lambda w: ops.pack_conv_weight(w, True, 1))
+    dx_last = torch.empty(n_img, IMG_PIX, C, device=dy.device, dtype=torch.float16)
+    ops.conv_gemm(wtt, dy_h, taps=1, cin=tail, cout=C, n_img=n_img, epi=EPI_PLAIN, out=dx_last, act=1)
+    return dx_last
 
 
 # ======================================================================================== multi-hop model
@@ -554,7 +608,8 @@ def tmh_generator_backward(P, cache, ctx, dfilm, q_input, q_lens32, sink):
     question_backward(P, ctx, None, q_input, q_lens32, sink, ctx["enc_prefix"], dh_steps=dstates)
 
 
-def tmh_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens_host, q_lens32, film_h, film_c, training, save):
+def tmh_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens_host, q_lens32, film_h, film_c, training, save,
+                prec=TF32):
     """TimeMultiHopFiLMPretrainedStem.forward (models/time_multi_hop_pt_stem.py:191-250): conv trunk with the
     multi-hop FiLM generator, then the global-pooling tail."""
     dev = v_input.device
@@ -562,12 +617,12 @@ def tmh_forward(P, bn, cache, v_input, q_input, v_lens_host, q_lens_host, q_lens
     plan = get_plan(v_lens_host, B, T, dev)
     max_q_len = int(max(q_lens_host))
     x, ctx = trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c, training, save,
-                           gen_fwd=lambda *a: tmh_generator_forward(*a, max_q_len=max_q_len))
+                           gen_fwd=lambda *a: tmh_generator_forward(*a, max_q_len=max_q_len), prec=prec)
     return _gp_tail_forward(P, cache, plan, x, ctx, B, T, save)
 
 
 def tmh_backward(P, cache, ctx, dlogits, q_input, q_lens32, grad_hook=None, grad_bucket=None):
     grads = GradSink(grad_hook, grad_bucket)
-    dx_last = _gp_tail_backward(P, ctx, dlogits, grads)
+    dx_last = _gp_tail_backward(P, cache, ctx, dlogits, grads)
     trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=tmh_generator_backward, mask_relu=False)
     return grads

@@ -2,10 +2,15 @@
 initialisation, the autograd bridge into videonavqa_b200.engine, and the carried question-LSTM state."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import engine, ops
+
+# operand storage of the tensor-core kernels when neither VNQA_OPERANDS nor set_operands() says otherwise
+DEFAULT_OPERANDS = "tf32"
 
 
 def reference_init(module):
@@ -171,6 +176,23 @@ class FilmModuleBase(nn.Module):
 
     def _finish(self, perm, h, c):
         self.film_hidden = (h[perm].unsqueeze(0), c[perm].unsqueeze(0))
+
+    # ---- operand precision of the tensor-core kernels ---------------------------------------------------------
+    @property
+    def precision(self):
+        """engine.Precision of this module: 'tf32' (fp32 storage, tf32 MMA operands) or 'fp16' (half trunk activations
+        and operands, twice the MMA rate; fp32 accumulation, statistics, LSTMs and gradients).  Default from the
+        environment variable VNQA_OPERANDS (DEFAULT_OPERANDS when unset); set with ``set_operands()``."""
+        p = self.__dict__.get("_precision")
+        if p is None:
+            p = engine.Precision(os.environ.get("VNQA_OPERANDS", DEFAULT_OPERANDS),
+                                 float(os.environ.get("VNQA_LOSS_SCALE", "4096")))
+            self.__dict__["_precision"] = p
+        return p
+
+    def set_operands(self, operands, loss_scale=4096.0):
+        self.__dict__["_precision"] = engine.Precision(operands, loss_scale)
+        return self
 
     def invalidate_weight_cache(self, registered_only=False):
         """Drop the packed-weight caches (engine.WeightCache).  Needed after the parameters were written through

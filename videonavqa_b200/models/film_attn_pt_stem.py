@@ -66,7 +66,7 @@ class FiLMAttnPretrainedStem(FilmModuleBase):
                                f"max_num_frames={self.max_num_frames} (out_linear width, SURVEY Q7)")
         v_host, q_lens32, perm, h, c, q_in = self._prepare(v_input, q_input, v_lens, q_lens)
         logits, ctx = engine.attn_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, q_lens32, h, c,
-                                          self.max_num_frames, self.training, save)
+                                          self.max_num_frames, self.training, save, prec=self.precision)
         self._finish(perm, h, c)
         ctx["q_in"], ctx["q_lens32"] = q_in, q_lens32
         return logits, ctx

@@ -52,7 +52,7 @@ class FiLMGlobalPoolingPretrainedStem(FilmModuleBase):
     def _forward_impl(self, P, v_input, q_input, v_lens, q_lens, save):
         v_host, q_lens32, perm, h, c, q_in = self._prepare(v_input, q_input, v_lens, q_lens)
         logits, ctx = engine.gp_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, q_lens32, h, c,
-                                        self.training, save)
+                                        self.training, save, prec=self.precision)
         self._finish(perm, h, c)
         ctx["q_in"], ctx["q_lens32"] = q_in, q_lens32
         return logits, ctx

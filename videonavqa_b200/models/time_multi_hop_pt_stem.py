@@ -56,7 +56,7 @@ class TimeMultiHopFiLMPretrainedStem(FilmModuleBase):
         v_host, q_lens32, perm, h, c, q_in = self._prepare(v_input, q_input, v_lens, q_lens)
         q_host = self._last_q_host
         logits, ctx = engine.tmh_forward(P, self._bn_state(), self._cache, v_input, q_in, v_host, q_host, q_lens32, h, c,
-                                         self.training, save)
+                                         self.training, save, prec=self.precision)
         self._finish(perm, h, c)
         ctx["q_in"], ctx["q_lens32"] = q_in, q_lens32
         return logits, ctx

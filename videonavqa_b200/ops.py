@@ -76,31 +76,44 @@ def device_check():
 
 
 # ------------------------------------------------------------------------------------------ layout / packing
-def frames_to_nhwc(v_input, img_of, n_img):
+def act_dtype(act):
+    """torch dtype of the tensor-core operand / trunk activation storage (include/vnqa_b200.h VNQA_ACT_*)."""
+    return torch.float16 if act else torch.float32
+
+
+def frames_to_nhwc(v_input, img_of, n_img, act=0):
     B, C, H, W, T = v_input.shape
     assert (H, W) == (10, 13)
-    x = torch.empty(n_img, IMG_PIX, C, device=v_input.device, dtype=torch.float32)
-    check(_lib.lib().vnqa_frames_to_nhwc(_p(_f32c(v_input)), _p(x), _p(img_of), B, C, T, _stream()), "frames_to_nhwc")
+    x = torch.empty(n_img, IMG_PIX, C, device=v_input.device, dtype=act_dtype(act))
+    check(_lib.lib().vnqa_frames_to_nhwc(_p(_f32c(v_input)), _p(x), _p(img_of), B, C, T, act, _stream()),
+          "frames_to_nhwc")
     return x
 
 
-def pack_conv_weight(w, transpose_flip=False):
-    """(Cout, Cin, kh, kw) -> [taps][rows_pad][K] tf32-rounded; transpose_flip builds the dgrad operand."""
+def to_half(x, scale=1.0):
+    """fp32 -> fp16 (times a power-of-two scale): tensors entering the fp16 domain."""
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    check(_lib.lib().vnqa_to_half(_p(_f32c(x)), _p(out), x.numel(), float(scale), _stream()), "to_half")
+    return out
+
+
+def pack_conv_weight(w, transpose_flip=False, act=0):
+    """(Cout, Cin, kh, kw) -> [taps][rows_pad][K] rounded to the operand type; transpose_flip builds the dgrad operand."""
     cout, cin = w.shape[0], w.shape[1]
     taps = w.shape[2] * w.shape[3]
     rows = cin if transpose_flip else cout
     K = cout if transpose_flip else cin
     rows_pad = round_up(rows, 128)
-    out = torch.empty(taps, rows_pad, K, device=w.device, dtype=torch.float32)
-    check(_lib.lib().vnqa_pack_conv_weight(_p(_f32c(w)), _p(out), cout, cin, taps, rows_pad, int(transpose_flip),
+    out = torch.empty(taps, rows_pad, K, device=w.device, dtype=act_dtype(act))
+    check(_lib.lib().vnqa_pack_conv_weight(_p(_f32c(w)), _p(out), cout, cin, taps, rows_pad, int(transpose_flip), act,
                                            _stream()), "pack_conv_weight")
     return out
 
 
-def pack_matrix(w, transpose=False):
+def pack_matrix(w, transpose=False, act=0):
     """Linear weight (N, K) as a 1-tap 'convolution' operand: [rows_pad][K] (or its transpose [K_pad][N])."""
     n, k = w.shape
-    return pack_conv_weight(w.view(n, k, 1, 1), transpose_flip=transpose)[0]
+    return pack_conv_weight(w.view(n, k, 1, 1), transpose_flip=transpose, act=act)[0]
 
 
 def permute_fc_weight(w, C, inverse=False, n_pad=None, out=None):
@@ -117,8 +130,11 @@ def permute_fc_weight(w, C, inverse=False, n_pad=None, out=None):
 # ------------------------------------------------------------------------------------------ tensor-core GEMMs
 def conv_gemm(w_packed, x, *, taps, cin, cout, n_img, epi, out, flat=False, x_ld=0, splits=1, no_round=False,
               bias=None, scale=None, shift=None, img_frame=None, stat_sum=None, stat_sq=None, film=None,
-              film_row=None, film_ld=0, alpha_off=0, res=None, z_out=None, add=None, dbias=None):
+              film_row=None, film_ld=0, alpha_off=0, res=None, z_out=None, add=None, dbias=None, act=0, out_f32=False,
+              grad_unscale=1.0):
+    assert x.dtype == act_dtype(act) and w_packed.dtype == act_dtype(act), (x.dtype, w_packed.dtype, act)
     a = ConvArgs()
+    a.act_dtype, a.out_f32, a.grad_unscale = act, int(out_f32), float(grad_unscale)
     a.w_packed = w_packed.data_ptr()
     a.x = x.data_ptr()
     a.taps, a.cin, a.cout, a.rows_pad, a.n_img = taps, cin, cout, round_up(cout, 128), n_img
@@ -136,13 +152,27 @@ def conv_gemm(w_packed, x, *, taps, cin, cout, n_img, epi, out, flat=False, x_ld
     return out
 
 
-def conv_wgrad(dy, x, dw, *, n_img, cout, cin, taps, flat=False):
+_WS_BYTES = {}
+
+
+def conv_wgrad(dy, x, dw, *, n_img, cout, cin, taps, flat=False, act=0, grad_unscale=1.0):
+    """dw (fp32, PyTorch layout) is overwritten; deterministic reduction order (csrc/wgrad.cu)."""
+    assert dy.dtype == act_dtype(act) and x.dtype == act_dtype(act) and dw.dtype == torch.float32 and dw.is_contiguous()
     rows = n_img if flat else n_img * IMG_PIX
     tag = f"conv_wgrad.{'flat' if flat else str(taps) + 'tap'}.k{cin}.n{cout}"
-    ws = torch.zeros(taps, cout, cin, device=dw.device, dtype=torch.float32) if taps != 1 else None
+    key = (cout, cin, taps)
+    if key not in _WS_BYTES:
+        zb = ctypes.c_int64(0)
+        total = _lib.lib().vnqa_conv_wgrad_ws_bytes(cout, cin, taps, ctypes.byref(zb))
+        if total < 0:
+            raise _lib.VnqaError(f"vnqa_conv_wgrad_ws_bytes rejected ({cout}, {cin}, {taps})")
+        _WS_BYTES[key] = (int(total), int(zb.value))
+    total, zero = _WS_BYTES[key]
+    ws = torch.empty(total, device=dw.device, dtype=torch.uint8)
+    ws[:zero].zero_()                       # turn counters (a few KB); the partial-sum area needs no initialisation
     with _timed(tag, 2.0 * rows * cout * cin * taps):
-        check(_lib.lib().vnqa_conv_wgrad(_p(dy), _p(x), _p(dw), _p(ws), n_img, cout, cin, taps, int(flat), _stream()),
-              "conv_wgrad")
+        check(_lib.lib().vnqa_conv_wgrad(_p(dy), _p(x), _p(dw), _p(ws), n_img, cout, cin, taps, int(flat), act,
+                                         float(grad_unscale), _stream()), "conv_wgrad")
     return dw
 
 
@@ -207,33 +237,36 @@ def bn_eval_affine(gamma, beta, running_mean, running_var, eps):
     return scale, shift
 
 
-def bn_apply(y, img_frame, scale, shift):
+def bn_apply(y, img_frame, scale, shift, act=0):
     n_img, _, C = y.shape
-    x = torch.empty_like(y)
-    with _timed("hbm.bn_apply", 2.0 * y.numel() * 4):
-        check(_lib.lib().vnqa_bn_apply(_p(y), _p(x), _p(img_frame), _p(scale), _p(shift), n_img, C, _stream()),
+    x = torch.empty(y.shape, device=y.device, dtype=act_dtype(act))
+    with _timed("hbm.bn_apply", float(y.numel() * (4 + x.element_size()))):
+        check(_lib.lib().vnqa_bn_apply(_p(y), _p(x), _p(img_frame), _p(scale), _p(shift), n_img, C, act, _stream()),
               "bn_apply")
     return x
 
 
-def bn_backward(dx, y, img_frame, frame_ct, n_frames, mean, rstd, gamma, dbias, dgamma, dbeta):
+def bn_backward(dx, y, img_frame, frame_ct, n_frames, mean, rstd, gamma, dbias, dgamma, dbeta, act=0,
+                grad_unscale=1.0):
     n_img, _, C = y.shape
+    assert dx.dtype == act_dtype(act) and y.dtype == torch.float32
     s1 = torch.empty(n_frames, C, device=y.device, dtype=torch.float32)
     s2 = torch.empty_like(s1)
-    dy = torch.empty_like(y)
+    dy = torch.empty(y.shape, device=y.device, dtype=act_dtype(act))
     check(_lib.lib().vnqa_bn_backward(_p(dx), _p(y), _p(img_frame), _p(frame_ct), n_frames, _p(mean), _p(rstd),
                                       _p(gamma), n_img, C, _p(s1), _p(s2), _p(dy), _p(dbias), _p(dgamma), _p(dbeta),
-                                      _stream()), "bn_backward")
+                                      act, float(grad_unscale), _stream()), "bn_backward")
     return dy
 
 
-def film_backward(dout, z, film, film_row, alpha_off, dfilm, dbias, mask_relu=True):
+def film_backward(dout, z, film, film_row, alpha_off, dfilm, dbias, mask_relu=True, act=0, grad_unscale=1.0):
     n_img, _, C = z.shape
+    assert dout.dtype == act_dtype(act) and z.dtype == act_dtype(act)
     dz = torch.empty_like(z)
-    with _timed("hbm.film_bwd", 3.0 * z.numel() * 4):
+    with _timed("hbm.film_bwd", 3.0 * z.numel() * z.element_size()):
         check(_lib.lib().vnqa_film_backward(_p(dout), _p(z), _p(film), _p(film_row), film.stride(0), alpha_off, n_img,
-                                            C, _p(dz), _p(dfilm), _p(dbias), int(mask_relu), _stream()),
-              "film_backward")
+                                            C, _p(dz), _p(dfilm), _p(dbias), int(mask_relu), act, float(grad_unscale),
+                                            _stream()), "film_backward")
     return dz
 
 
