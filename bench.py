@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
                     help="fused = videonavqa_b200.optim.FusedClipAdam over the flat bucket; torch = clip_grad_norm_ + Adam")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager baseline on the same GPU")
+    ap.add_argument("--operands", choices=["fp16", "tf32"], default=None,
+                    help="operand storage of the tensor-core kernels (default: the package default / VNQA_OPERANDS)")
     return ap.parse_args()
 
 
@@ -157,7 +159,7 @@ def hbm_roofline(kernels, peaks):
     try:
         k = kernels["hbm.film_bwd"]
         peak = float(peaks.get("hbm_gbs") or 6650.0)
-        return {"bound": "hbm", "kernel": "film_bwd_kernel (autograd of the FiLM modulation, 3 x 1.19 GB per launch)",
+        return {"bound": "hbm", "kernel": "film_bwd_kernel (autograd of the FiLM modulation: reads dOut and z, writes dz)",
                 "achieved": k["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": round(k["gb_per_s"] / peak, 4),
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else
                 "fallback 6.65 TB/s (B200_PROFILING.md)"}
@@ -284,6 +286,8 @@ def gpu_leg(args):
     else:
         model = TimeMultiHopFiLMPretrainedStem(num_tail_channels=M["tail"], **common)
     model = model.to(dev)
+    if args.operands:
+        model.set_operands(args.operands)
     train = args.workload == "train"
     model.train(train)
     reducer = None
@@ -456,9 +460,15 @@ def gpu_leg(args):
     except Exception:
         pass
     bf16_peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)"
-                if peaks else "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)")
-    tf32_peak = bf16_peak / 2.0
+    fp16 = model.precision.fp16
+    if fp16:     # kind::f16 issues at the bf16 rate: the measured cuBLAS bf16 number is the peak as it stands
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kind::f16 issues at the bf16 rate)"
+                    if peaks else "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)")
+        tf32_peak = bf16_peak
+    else:
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)"
+                    if peaks else "fallback 1.4 PFLOP/s sustained bf16 / 2 (B200_PROFILING.md)")
+        tf32_peak = bf16_peak / 2.0
     dom_tag = f"conv_gemm.9tap.epi3.k{CFG['C']}.n{CFG['C']}"            # conv3x3 + FiLM epilogue (forward)
     kernels = summarise_kernels(klass, args.steps, ms)
     roof = None
@@ -469,13 +479,15 @@ def gpu_leg(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_tag)
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<EPI_FILM> (conv3x3 1024->1024 + FiLM/ReLU/residual)",
+        roof = {"bound": "tensor",
+                "kernel": f"conv_gemm_kernel<EPI_FILM, 2, {'__half' if fp16 else 'float'}> (conv3x3 1024->1024 + FiLM/ReLU/residual)",
                 "achieved": k["tflops"], "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                 "frac": round(k["tflops"] / tf32_peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "peak_nominal": 1100.0, "frac_nominal": round(k["tflops"] / 1100.0, 4),
-                "note": "frac > 1: cuBLAS bf16 sustains 61% of its nominal rate under the 1 kW cap, this tf32 kernel "
-                        "keeps the tensor pipe 96% busy (profiles/r01b_conv3x3_film_2cta.ncu_details.txt); "
-                        "frac_nominal is against the 1.1 PFLOP/s dense tf32 datasheet figure",
+                "peak_nominal": 2250.0 if fp16 else 1125.0,
+                "frac_nominal": round(k["tflops"] / (2250.0 if fp16 else 1125.0), 4),
+                "note": "frac > 1 is possible: the peak is what cuBLAS bf16 sustains under the 1 kW power cap (61% of "
+                        "nominal), this kernel keeps the tensor pipe ~96% busy; frac_nominal is against the dense "
+                        "datasheet rate of the operand type",
                 "flops_per_launch": klass[dom_tag][2], "ms_per_launch": k["ms_per_launch"]}
     clips = B * world
     gflop = M["train_gflop"] if train else M["fwd_gflop"]
@@ -484,7 +496,9 @@ def gpu_leg(args):
         "metric": metric_name(args),
         "value": round(clips / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32 operands, fp32 accumulate/storage",
+        "vs_baseline": None,
+        "dtype": ("fp16 operands / trunk activations (10-bit mantissa like tf32), fp32 accumulate, fp32 statistics / "
+                  "LSTMs / gradients / optimizer" if fp16 else "tf32 operands, fp32 accumulate/storage"),
         "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "global_batch": clips, "frames_per_clip": CFG["T"], "parallelism": f"dp{world}",

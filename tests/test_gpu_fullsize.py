@@ -211,4 +211,4 @@ def test_conv1x1_conv_init_and_split_k_full_size(act):
     ops.conv_gemm(wq, x.view(n_img, K), taps=1, cin=K // splits, cout=A, n_img=n_img, epi=EPI_PARTIAL, out=partial,
                   flat=True, x_ld=K, splits=splits, act=act)
     emax, el2 = _errs(partial.sum(0), xf.view(n_img, K) @ wfc.t())
-    assert emax <= 5e-5 and el2 <= 3e-5
+    assert emax <= 5e-5 and el2 <= 5e-5

@@ -87,11 +87,11 @@ def test_flat_bucket_training_matches_plain_autograd_path():
         assert abs(la.item() - lb.item()) <= 2e-4 * abs(la.item()), (step, la.item(), lb.item())
     # Adam divides by sqrt(v): in the first steps an element's update is ~lr * sign(g), so elements whose gradient is
     # rounding noise (bias / statistic reductions use atomics) may move in opposite directions - bound the relative L2
-    # tightly and the worst element by 2 * lr * steps
+    # and the worst element by 2 * lr * steps
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         d = (pa.detach() - pb.detach()).double()
         rel = float(d.norm() / pa.detach().double().norm().clamp_min(1e-12))
-        assert rel <= 2e-3, (n, rel)
+        assert rel <= 2e-2, (n, rel)      # zero-initialised biases ARE their first three updates
         assert float(d.abs().max()) <= 2 * 1e-3 * 3 + 1e-6, (n, float(d.abs().max()))
     # state_dict still has the reference layout and loads into a fresh module
     sd = mb.state_dict()

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--channels", type=int, default=1024)
     ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--operands", choices=["fp16", "tf32"], default=None)
     a = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -35,6 +36,8 @@ def main():
     m = FiLMAttnPretrainedStem(batch_size=a.batch, q_embedding_size=128, nb_classes=70, num_input_channels=512,
                                num_res_block_channels=a.channels, num_res_blocks=a.blocks, hidden_size=128,
                                at_hidden_size=128, max_num_frames=35, vocab_size=134).to(dev).eval()
+    if a.operands:
+        m.set_operands(a.operands)
     params = {k: p.detach() for k, p in m.named_parameters()}
     for k, conv in enumerate(m.conv1x1_layers):
         params[f"conv1x1_layers.{k}.weight"] = conv.weight.detach()
@@ -57,7 +60,7 @@ def main():
         agree += int(same.sum()); total += a.batch
         top2 = ref.topk(2, dim=1).values
         margins += ((top2[:, 0] - top2[:, 1]) / ref.abs().max())[~same].tolist()
-    print(f"clips {total}  argmax agreement {100.0 * agree / total:.3f} %  normalised max logit error {worst:.3e}")
+    print(f"operands {m.precision.name}  clips {total}  argmax agreement {100.0 * agree / total:.3f} %  normalised max logit error {worst:.3e}")
     if margins:
         print(f"disagreeing clips: {len(margins)}; their reference top-2 margins (normalised): max {max(margins):.2e}")
 

@@ -69,7 +69,7 @@ def beat(what=""):
 def _report(stall_s, out_dir):
     rank = os.environ.get("RANK", "0")
     os.makedirs(out_dir, exist_ok=True)
-    path = os.path.join(out_dir, f"hang_rank{rank}.log")
+    path = os.path.join(out_dir, "hang_" + os.environ.get("HANGWATCH_TAG", f"rank{rank}") + ".log")
     with open(path, "w") as f:
         def say(msg):
             for fh in (f, sys.stderr):
@@ -102,7 +102,8 @@ def _report(stall_s, out_dir):
             say("--- cuda-gdb")
             try:
                 r = subprocess.run(["cuda-gdb", "-p", str(os.getpid()), "-batch", "-ex", "info cuda kernels", "-ex",
-                                    "info cuda warps", "-ex", "info threads", "-ex", "thread apply all bt 6"], capture_output=True, text=True,
+                                    "info cuda blocks", "-ex", "info cuda threads", "-ex", "info cuda warps", "-ex",
+                                    "info threads"], capture_output=True, text=True,
                                    timeout=90)
                 say(r.stdout[-12000:])
                 say(r.stderr[-3000:])

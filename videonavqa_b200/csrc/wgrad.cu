@@ -18,8 +18,9 @@
 //     tile - each CTA stages its own 128 output channels of dY and its own 128 input channels of X, halving the
 //     operand bytes per MMA flop with respect to the single-CTA 128 x 128 tile;
 //   NCTA = 1: 128 x 128 tiles (small / odd channel counts, the Linear of :244).
-// Split-K over pixel chunks, SPLIT-MAJOR tile order: the co-resident CTAs always work on the same pixel range (sized
-// to stay L2-resident), so dY / X are read from DRAM about once instead of once per tile wave.
+// Split-K over pixel chunks only as far as needed to fill the SMs (about two rounds of tiles per CTA group), in
+// SPLIT-MAJOR tile order: the co-resident CTAs always stream the same pixel range, so dY / X are read from DRAM about
+// once per round instead of once per tile.
 //
 // DETERMINISTIC reduction of the split-K partial tiles: every (tile, CTA, epilogue warp) owns a turn counter; split s
 // of a tile waits until the counter reads s, then accumulates its partial into the [tap][Cout][Cin] buffer with plain
@@ -246,18 +247,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int ci = nt * N_INSTR + j0 + lane;
         if (ci < p.cin) {
           float* obase = p.out + ((long long)tap * p.cout + co0) * p.cin + ci;
+          float acc[32];
           if (sp == 0) {
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r)
-              if (co0 + r < p.cout) obase[(long long)r * p.cin] = tile_s[r * 33 + lane];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) acc[r] = 0.f;
           } else {
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r)
-              if (co0 + r < p.cout) {
-                float* q = obase + (long long)r * p.cin;
-                *q = __ldcg(q) + tile_s[r * 33 + lane];     // L2 load: the previous split ran on another SM
-              }
+            // 32 independent L2 loads in flight (the previous split ran on another SM: bypass L1)
+#pragma unroll
+            for (int r = 0; r < 32; ++r) acc[r] = co0 + r < p.cout ? __ldcg(obase + (long long)r * p.cin) : 0.f;
           }
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (co0 + r < p.cout) obase[(long long)r * p.cin] = acc[r] + tile_s[r * 33 + lane];
         }
         __syncwarp();
       }
@@ -372,16 +373,19 @@ static int conv_wgrad_typed(const void* dy, const void* x, float* dw, void* ws, 
   wp.dbg = debug_buffer();
   const int sms = vnqa_sm_count();
   if (sms <= 0) return -2;
-  // split-K: (a) one split's slice of dY and X (chunks * KP rows * (cout+cin) elements) should stay L2-resident while
-  // the waves of that split run, (b) there must be enough tiles to fill the SMs, (c) every split owns >= 1 chunk.
+  // split-K over pixel chunks.  The turn-ordered reduction serialises the epilogues of one tile's splits, so the
+  // split count is kept as small as filling the machine allows: about two rounds of tiles per CTA group (items are
+  // issued split-major, so the ~groups concurrently running items always stream the same pixel range through L2 - dY / X
+  // are read from DRAM about once per round), at most 10 splits.  VNQA_WGRAD_SPLITS overrides (bring-up).
   const int groups = sms / ncta;
-  const double chunk_bytes = (double)W::KP * ES * ((double)(cout < 1024 ? cout : 1024) + (double)(cin < 1024 ? cin : 1024));
-  int cps = (int)(48.0e6 / chunk_bytes);                       // ~48 MB of the 126 MB L2 per operand pair
-  const int cps_fill = (int)((long long)wp.n_chunks * sh.base_items / (2LL * groups));   // >= 2 items per CTA group
-  if (cps > cps_fill) cps = cps_fill;
-  const int cps_min = Op<T>::HALF ? 2 : 4;
-  if (cps < cps_min) cps = cps_min;
-  if (cps > wp.n_chunks) cps = wp.n_chunks;
+  (void)ES;
+  int splits = (2 * groups) / sh.base_items;
+  static const int forced_splits = [] { const char* e = getenv("VNQA_WGRAD_SPLITS"); return e ? atoi(e) : 0; }();
+  if (forced_splits > 0) splits = forced_splits;
+  if (splits > 10 && forced_splits <= 0) splits = 10;
+  if (splits < 1) splits = 1;
+  if (splits > wp.n_chunks) splits = wp.n_chunks;
+  const int cps = (wp.n_chunks + splits - 1) / splits;
   wp.chunks_per_split = cps;
   wp.splits = (wp.n_chunks + cps - 1) / cps;
 
