@@ -1,0 +1,43 @@
+"""Stages the UNMODIFIED reference drivers (and the out-of-scope `models.*` modules they import) under oracle/_ref/ so
+that the driver-compatibility test can execute them on the GPU box, where /root/reference does not exist.
+
+TEST INFRASTRUCTURE ONLY.  Nothing is edited: files are copied byte for byte from the reference tree into
+oracle/_ref/reference/ (git-ignored, travels to the GPU box with the snapshot; never part of the product, never
+imported by videonavqa_b200).  Run by __graft_entry__.build() when /root/reference is present:
+
+    python oracle/stage_ref.py [/root/reference]
+
+Staged:
+  eval/q_and_v_eval.py, eval/q_and_v_test.py   the train / validate and test drivers
+  eval/utils.py, eval/dataset.py               constants, per-class accuracy, the mp4 / question loader
+  models/__init__.py, mac.py, q_concat_*.py, obj_detector.py   imported by the drivers, out of scope for the product
+The three hot-path modules (film_attn_pt_stem, film_global_pooling_pt_stem, time_multi_hop_pt_stem) are NOT staged:
+the drivers get them from dropin/models (the B200 implementations).
+"""
+import hashlib
+import json
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = ["eval/q_and_v_eval.py", "eval/q_and_v_test.py", "eval/utils.py", "eval/dataset.py", "models/__init__.py",
+         "models/mac.py", "models/q_concat_cnn2d_lstm.py", "models/q_concat_cnn3d.py", "models/obj_detector.py"]
+
+
+def stage(ref="/root/reference"):
+    dst_root = os.path.join(HERE, "_ref", "reference")
+    manifest = {}
+    for rel in FILES:
+        src = os.path.join(ref, rel)
+        dst = os.path.join(dst_root, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(src, dst)
+        manifest[rel] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
+    with open(os.path.join(dst_root, "MANIFEST.json"), "w") as f:
+        json.dump({"source": ref, "sha256": manifest}, f, indent=1)
+    return dst_root
+
+
+if __name__ == "__main__":
+    print(stage(sys.argv[1] if len(sys.argv) > 1 else "/root/reference"))

@@ -373,16 +373,23 @@ static int conv_wgrad_typed(const void* dy, const void* x, float* dw, void* ws, 
   wp.dbg = debug_buffer();
   const int sms = vnqa_sm_count();
   if (sms <= 0) return -2;
-  // split-K over pixel chunks.  The turn-ordered reduction serialises the epilogues of one tile's splits, so the
-  // split count is kept as small as filling the machine allows: about two rounds of tiles per CTA group (items are
-  // issued split-major, so the ~groups concurrently running items always stream the same pixel range through L2 - dY / X
-  // are read from DRAM about once per round), at most 10 splits.  VNQA_WGRAD_SPLITS overrides (bring-up).
+  // split-K over pixel chunks.  Two lower bounds on the split count:
+  //  (a) fill: about two rounds of tiles per CTA group (items are issued split-major, so the ~groups concurrently
+  //      running items always stream the same pixel range through L2 - dY / X are read from DRAM about once per round);
+  //  (b) precision: the tensor core accumulates in fp32 with truncation, a biased error that grows linearly with the
+  //      length of one accumulation chain (measured: 1.2e-5 normalised at 5.8k pixel rows, 6.9e-4 at 291k); chains are
+  //      therefore bounded to ~29k pixel rows (<= 1e-4) and the partial tiles are added in round-to-nearest fp32.
+  // The turn-ordered reduction serialises the epilogues of one tile's splits, so no more splits than that (<= 16).
+  // VNQA_WGRAD_SPLITS overrides (bring-up).
   const int groups = sms / ncta;
   (void)ES;
+  constexpr int MAX_CHAIN_CHUNKS = 29120 / W::KP;       // 280 (tf32) / 140 (fp16) chunks
   int splits = (2 * groups) / sh.base_items;
+  const int by_chain = (wp.n_chunks + MAX_CHAIN_CHUNKS - 1) / MAX_CHAIN_CHUNKS;
+  if (splits < by_chain) splits = by_chain;
+  if (splits > 16) splits = 16;
   static const int forced_splits = [] { const char* e = getenv("VNQA_WGRAD_SPLITS"); return e ? atoi(e) : 0; }();
   if (forced_splits > 0) splits = forced_splits;
-  if (splits > 10 && forced_splits <= 0) splits = 10;
   if (splits < 1) splits = 1;
   if (splits > wp.n_chunks) splits = wp.n_chunks;
   const int cps = (wp.n_chunks + splits - 1) / splits;

@@ -25,6 +25,24 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+class _Nvtx:
+    """NVTX range per op group (SURVEY.md §5 tracing), on when VNQA_NVTX=1: shows the stages of a step in Nsight
+    Systems / Compute timelines; a no-op otherwise."""
+
+    on = os.environ.get("VNQA_NVTX") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_pop()
+
+
 class Precision:
     """Operand / trunk-activation storage of the tensor-core kernels (include/vnqa_b200.h VNQA_ACT_*).
 
@@ -216,13 +234,14 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
     act, pk = prec.act, prec.key
 
     # K0: frame-image-major NHWC
-    x0 = ops.frames_to_nhwc(v_input, plan.img_of, n_img, act)
+    with _Nvtx("vnqa.K0.frames_to_nhwc"):
+        x0 = ops.frames_to_nhwc(v_input, plan.img_of, n_img, act)
 
     # ---- question encoder on a side stream (independent of the video until the first FiLM epilogue)
     main = torch.cuda.current_stream()
     side = _side_stream(dev)
     side.wait_stream(main)
-    with torch.cuda.stream(side):
+    with torch.cuda.stream(side), _Nvtx("vnqa.K6.film_generator.fwd"):
         film, gctx = gen_fwd(P, cache, plan, q_input, q_lens32, film_h, film_c, save, nb, C)
         film.record_stream(main)        # allocated on the side stream, consumed on the main stream
         for t in gctx.values():
@@ -255,6 +274,8 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
     # ---- FiLM ResBlocks (:217-241)
     xs, ress, zs = [x], [], []
     for k in range(nb):
+        if _Nvtx.on:
+            torch.cuda.nvtx.mark(f"vnqa.resblock.{k}.fwd")
         w1 = cache.get(f"{pk}c1x1.{k}", P[f"conv1x1_layers.{k}.weight"], pack)
         w3 = cache.get(f"{pk}c3x3.{k}", P[f"film_pipeline.{k}.weight"], pack)
         res = torch.empty_like(x)
@@ -311,7 +332,7 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
         convolution backward: runs on the side stream as soon as dfilm is complete (after block 0's FiLM backward)."""
         nonlocal gen_done
         side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), _Nvtx("vnqa.K6.film_generator.bwd"):
             local = GradSink(None, grads._bucket if isinstance(grads, GradSink) else None)
             gen_bwd(P, cache, ctx, dfilm, q_input, q_lens32, local)
             for t in local.values():
@@ -323,6 +344,8 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
     if nb == 0:
         generator_backward()
     for k in reversed(range(nb)):
+        if _Nvtx.on:
+            torch.cuda.nvtx.mark(f"vnqa.resblock.{k}.bwd")
         res, z, x_in = ctx["ress"][k], ctx["zs"][k], ctx["xs"][k]
         db3 = grads.buffer(f"film_pipeline.{k}.bias", P[f"film_pipeline.{k}.bias"])
         dz = ops.film_backward(dout, z, film, plan.film_row, 2 * k * C, dfilm, db3, mask_relu=mask_relu, act=act,
