@@ -39,7 +39,7 @@ ZERO_GRAD = ("fc_hidden_attn.weight", "fc_hidden_attn.bias", "fc_attn_1.bias")
 def _module(B, seed, train):
     from videonavqa_b200.models import FiLMAttnPretrainedStem
     torch.manual_seed(seed)
-    m = FiLMAttnPretrainedStem(batch_size=B, **CFG).cuda()
+    m = FiLMAttnPretrainedStem(batch_size=B, **CFG).cuda().set_operands("tf32")   # tests/test_gpu_fp16.py re-sets fp16
     # non-trivial biases / BatchNorm affine so that their gradients are exercised
     with torch.no_grad():
         for n, p in m.named_parameters():

@@ -35,6 +35,12 @@ def test_frames_to_nhwc_is_exact_tf32_rounding():
         ref = O.tf32_round(v[b, :, :, :, t].permute(1, 2, 0).reshape(130, C).contiguous())
         assert torch.equal(x[int(img_of[b, t])], ref)
     assert int((img_of >= 0).sum()) == plan.n_img == sum(v_lens)
+    # fp16 operand storage: round-to-nearest-even to half, same layout
+    xh = ops.frames_to_nhwc(v.cuda(), plan.img_of, plan.n_img, act=1).cpu()
+    assert xh.dtype == torch.float16
+    for b, t in ((0, 0), (0, 34), (1, 19), (3, 6), (4, 0)):
+        ref = v[b, :, :, :, t].permute(1, 2, 0).reshape(130, C).contiguous().half()
+        assert torch.equal(xh[int(img_of[b, t])], ref)
 
 
 def test_sgemm_variants_match_fp64():

@@ -30,8 +30,9 @@ def _cls(kind):
             "tmh": TimeMultiHopFiLMPretrainedStem}[kind]
 
 
-def build_module(kind, kw, params):
-    m = _cls(kind)(**kw)
+def build_module(kind, kw, params, operands="tf32"):
+    """The tests of this file pin the tf32 path explicitly (the package default is fp16, tests/test_gpu_fp16.py)."""
+    m = _cls(kind)(**kw).set_operands(operands)
     sd = {k: v for k, v in params.items() if not k.startswith("conv1x1_layers")}
     res = m.load_state_dict(sd, strict=False)
     assert not res.unexpected_keys and all(k.startswith("bn_init.") for k in res.missing_keys), res
@@ -168,7 +169,7 @@ def test_full_size_logits_against_oracle():
     B = 2
     m = FiLMAttnPretrainedStem(batch_size=B, q_embedding_size=128, nb_classes=70, num_input_channels=512,
                                num_res_block_channels=1024, num_res_blocks=5, hidden_size=128, at_hidden_size=128,
-                               max_num_frames=35, vocab_size=134).cuda().eval()
+                               max_num_frames=35, vocab_size=134).cuda().eval().set_operands("tf32")
     v, q, _, q_lens, _ = O.synthetic_batch(B, seed=5)
     v_lens = torch.tensor([9, 4])
     params = {k: p.detach().cpu() for k, p in all_named_params(m).items()}
@@ -188,7 +189,7 @@ def test_full_size_multi_hop_logits_against_oracle():
     B = 2
     m = TimeMultiHopFiLMPretrainedStem(batch_size=B, q_embedding_size=128, nb_classes=70, num_input_channels=512,
                                        num_res_block_channels=1024, num_res_blocks=3, num_tail_channels=64,
-                                       hidden_size=128, vocab_size=134).cuda().eval()
+                                       hidden_size=128, vocab_size=134).cuda().eval().set_operands("tf32")
     v, q, _, q_lens, _ = O.synthetic_batch(B, seed=7)
     v_lens = torch.tensor([6, 3])
     params = {k: p.detach().cpu() for k, p in all_named_params(m).items()}

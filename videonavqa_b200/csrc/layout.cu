@@ -1,30 +1,65 @@
 // K0 and weight-layout kernels (HBM-bound data movement).
 #include "common.h"
+#include "optype.cuh"
 #include "stream_f16.h"
 #include "ptx.cuh"
 
 namespace vnqa {
 
-// (B, C, 130, T) with T innermost -> [img][130][C].  One block per (clip, pixel, 32-channel slab): the slab
-// [32 c][T] is read as 32 runs of T contiguous floats, transposed through shared memory and written as T runs of
-// 32 contiguous channels (128 B).  Replaces v_input[:ct, :, :, :, i] of models/film_attn_pt_stem.py:210.
-__global__ void __launch_bounds__(256) frames_to_nhwc_kernel(const float* __restrict__ v, float* __restrict__ x,
-                                                             const int* __restrict__ img_of, int C, int T) {
-  __shared__ float tile[32][65];
-  const int p = blockIdx.x;   // pixel 0..129
+// K0: (B, C, 130, T) fp32 with T innermost -> [img][130][C] in the operand type (replaces v_input[:ct, :, :, :, i] of
+// models/film_attn_pt_stem.py:210).  One block per (image row h, 128-byte channel slab, clip): for one channel the
+// 13 pixels x T frames of an image row are ONE contiguous run of 13*T floats (1820 B at T = 35) in v_input, so the
+// block reads 32 / 64 long runs (round 1 read 140-byte runs and reached 0.35 of the HBM roofline), converts into a
+// [slab][13*T] shared tile with an odd pitch (conflict-free column reads) and writes 13*T runs of 128 contiguous bytes.
+template <typename T, int CH>
+__global__ void __launch_bounds__(256) frames_to_nhwc_rows_kernel(const float* __restrict__ v, T* __restrict__ x,
+                                                                  const int* __restrict__ img_of, int C, int Tn,
+                                                                  int pitch) {
+  extern __shared__ uint8_t k0_raw[];
+  T* tile = reinterpret_cast<T*>(k0_raw);
+  const int h = blockIdx.x;   // image row 0..9
   const int cs = blockIdx.y;  // channel slab
   const int b = blockIdx.z;
-  const float* src = v + (((long long)b * C + cs * 32) * VNQA_IMG_PIX + p) * T;
-  for (int i = threadIdx.x; i < 32 * T; i += blockDim.x) {
-    const int c = i / T, t = i - c * T;
-    tile[c][t] = __ldg(src + (long long)c * VNQA_IMG_PIX * T + t);
+  const int run = VNQA_IMG_W * Tn;
+  const int nc = min(CH, C - cs * CH);   // the last slab may be partial (C is a multiple of 32)
+  const float* src = v + (((long long)b * C + cs * CH) * VNQA_IMG_PIX + h * VNQA_IMG_W) * Tn;
+  for (int i = threadIdx.x; i < nc * run; i += blockDim.x) {
+    const int c = i / run, j = i - c * run;
+    Op<T>::st(tile + c * pitch + j, __ldg(src + (long long)c * VNQA_IMG_PIX * Tn + j), 0);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  for (int t = threadIdx.x >> 5; t < T; t += blockDim.x >> 5) {
-    const int img = __ldg(img_of + b * T + t);
-    if (img >= 0) x[((long long)img * VNQA_IMG_PIX + p) * C + cs * 32 + lane] = tf32_round(tile[lane][t]);
+  constexpr int PER_LANE = CH / 32;      // 1 float or 2 halves per lane: 128 B per warp store
+  if (PER_LANE * lane >= nc) return;
+  for (int idx = threadIdx.x >> 5; idx < run; idx += blockDim.x >> 5) {
+    const int px = idx / Tn, t = idx - px * Tn;
+    const int img = __ldg(img_of + b * Tn + t);
+    if (img < 0) continue;
+    T* dst = x + ((long long)img * VNQA_IMG_PIX + h * VNQA_IMG_W + px) * C + cs * CH + PER_LANE * lane;
+    if (PER_LANE == 1) {
+      dst[0] = tile[lane * pitch + idx];
+    } else {
+      const T a = tile[(2 * lane) * pitch + idx], bb = tile[(2 * lane + 1) * pitch + idx];
+      T pair[2] = {a, bb};
+      *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(pair);
+    }
   }
+}
+
+template <typename T, int CH>
+static int launch_k0(const float* v_input, void* x_out, const int32_t* img_of, int B, int C, int Tn, cudaStream_t st) {
+  const int pitch = (VNQA_IMG_W * Tn) | 1;
+  const int smem = CH * pitch * (int)sizeof(T);
+  static int max_smem = 0;
+  if (smem > max_smem) {
+    VNQA_CHECK_CUDA(cudaFuncSetAttribute(frames_to_nhwc_rows_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem));
+    max_smem = smem;
+  }
+  dim3 grid(VNQA_IMG_H, (C + CH - 1) / CH, B);
+  frames_to_nhwc_rows_kernel<T, CH><<<grid, 256, smem, st>>>(v_input, reinterpret_cast<T*>(x_out), img_of, C, Tn, pitch);
+  VNQA_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // (Cout, Cin, taps) -> [tap][rows_pad][Cin]   (forward operand), or
@@ -72,17 +107,13 @@ __global__ void permute_fc_weight_kernel(const float* __restrict__ w, float* __r
 
 using namespace vnqa;
 
-extern "C" int vnqa_frames_to_nhwc(const float* v_input, void* x_out_, const int32_t* img_of, int32_t B, int32_t C,
+extern "C" int vnqa_frames_to_nhwc(const float* v_input, void* x_out, const int32_t* img_of, int32_t B, int32_t C,
                                    int32_t T, int32_t act_dtype, void* stream) {
-  VNQA_REQUIRE(v_input && x_out_ && img_of, "vnqa_frames_to_nhwc: null pointer");
-  if (act_dtype == VNQA_ACT_FP16) return frames_to_nhwc_h(v_input, x_out_, img_of, B, C, T, as_stream(stream));
-  float* x_out = static_cast<float*>(x_out_);
+  VNQA_REQUIRE(v_input && x_out && img_of, "vnqa_frames_to_nhwc: null pointer");
   VNQA_REQUIRE(C % 32 == 0 && C > 0, "vnqa_frames_to_nhwc: C must be a multiple of 32 (got %d)", C);
   VNQA_REQUIRE(T > 0 && T <= 64 && B > 0 && B <= 65535, "vnqa_frames_to_nhwc: bad B/T (%d, %d)", B, T);
-  dim3 grid(VNQA_IMG_PIX, C / 32, B);
-  frames_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(v_input, x_out, img_of, C, T);
-  VNQA_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return act_dtype == VNQA_ACT_FP16 ? launch_k0<__half, 64>(v_input, x_out, img_of, B, C, T, as_stream(stream))
+                                    : launch_k0<float, 32>(v_input, x_out, img_of, B, C, T, as_stream(stream));
 }
 
 extern "C" int vnqa_pack_conv_weight(const float* w, void* packed_, int32_t cout, int32_t cin, int32_t taps,

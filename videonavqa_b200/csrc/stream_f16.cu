@@ -1,4 +1,4 @@
-// HBM-bound kernels that touch trunk activations, fp16 storage (VNQA_ACT_FP16): K0 (layout transform), bn_apply,
+// HBM-bound kernels that touch trunk activations, fp16 storage (VNQA_ACT_FP16): bn_apply,
 // bn_backward, film_backward, weight packing and fp32 -> fp16 conversion.  Same arithmetic as their fp32 namesakes in
 // layout.cu / small.cu (fp32 math, fp16 loads/stores, 16-byte accesses); reached through the same C entry points,
 // which dispatch on act_dtype.  Backward signals are stored multiplied by a power-of-two loss scale; everything that
@@ -26,39 +26,6 @@ __device__ __forceinline__ Half8 pack8(const float* f) {
 __device__ __forceinline__ Half8 ldg8(const Half8* p) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
   return *reinterpret_cast<const Half8*>(&u);
-}
-
-// K0 (replaces v_input[:ct, :, :, :, i] of models/film_attn_pt_stem.py:210), row-tiled: one block per (image row h, 64-channel slab, clip).  For one channel the 13 pixels x T frames
-// of an image row are ONE contiguous run of 13*T floats (1820 B at T = 35) in v_input, so the block reads 64 long runs
-// instead of 64 x 13 runs of 140 B, converts to fp16 into a [64][13*T] shared tile (odd pitch in 32-bit words ->
-// conflict-free column reads) and writes 13*T runs of 64 channels (128 B per warp store).
-__global__ void __launch_bounds__(256) frames_to_nhwc_h_rows_kernel(const float* __restrict__ v, __half* __restrict__ x,
-                                                                    const int* __restrict__ img_of, int C, int T,
-                                                                    int pitch) {
-  extern __shared__ __half k0_tile[];
-  const int h = blockIdx.x;   // image row 0..9
-  const int cs = blockIdx.y;  // channel slab
-  const int b = blockIdx.z;
-  const int run = VNQA_IMG_W * T;
-  const int nc = min(64, C - cs * 64);
-  const float* src = v + (((long long)b * C + cs * 64) * VNQA_IMG_PIX + h * VNQA_IMG_W) * T;
-  for (int i = threadIdx.x; i < nc * run; i += blockDim.x) {
-    const int c = i / run, j = i - c * run;
-    k0_tile[c * pitch + j] = __float2half_rn(__ldg(src + (long long)c * VNQA_IMG_PIX * T + j));
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  if (2 * lane >= nc) return;
-  for (int idx = threadIdx.x >> 5; idx < run; idx += blockDim.x >> 5) {
-    const int px = idx / T, t = idx - px * T;
-    const int img = __ldg(img_of + b * T + t);
-    if (img >= 0) {
-      __half2 o;
-      o.x = k0_tile[(2 * lane) * pitch + idx];
-      o.y = k0_tile[(2 * lane + 1) * pitch + idx];
-      *reinterpret_cast<__half2*>(x + ((long long)img * VNQA_IMG_PIX + h * VNQA_IMG_W + px) * C + cs * 64 + 2 * lane) = o;
-    }
-  }
 }
 
 // x[row][c] = fp16(y[row][c] * scale[frame(img)][c] + shift[frame(img)][c]); 8 channels per thread
@@ -244,23 +211,6 @@ __global__ void to_half_kernel(const float* __restrict__ in, __half* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-int frames_to_nhwc_h(const float* v_input, void* x_out, const int32_t* img_of, int B, int C, int T, cudaStream_t st) {
-  VNQA_REQUIRE(C % 32 == 0 && C > 0, "vnqa_frames_to_nhwc: C must be a multiple of 32 (got %d)", C);
-  VNQA_REQUIRE(T > 0 && T <= 64 && B > 0 && B <= 65535, "vnqa_frames_to_nhwc: bad B/T (%d, %d)", B, T);
-  // halves per channel row; odd, so lanes reading rows 2*lane (+1) at one column hit 32 different banks
-  const int pitch = (VNQA_IMG_W * T) | 1;
-  const int smem = 64 * pitch * (int)sizeof(__half);
-  static int max_smem = 0;
-  if (smem > max_smem) {
-    VNQA_CHECK_CUDA(cudaFuncSetAttribute(frames_to_nhwc_h_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    max_smem = smem;
-  }
-  dim3 grid(VNQA_IMG_H, (C + 63) / 64, B);
-  frames_to_nhwc_h_rows_kernel<<<grid, 256, smem, st>>>(v_input, reinterpret_cast<__half*>(x_out), img_of, C, T, pitch);
-  VNQA_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 int pack_conv_weight_h(const float* w, void* packed, int cout, int cin, int taps, int rows_pad, int transpose_flip,
                        cudaStream_t st) {
   const long long total = (long long)taps * rows_pad * (transpose_flip ? cout : cin);

@@ -6,7 +6,6 @@
 #include <cuda_runtime.h>
 
 namespace vnqa {
-int frames_to_nhwc_h(const float* v_input, void* x_out, const int32_t* img_of, int B, int C, int T, cudaStream_t st);
 int pack_conv_weight_h(const float* w, void* packed, int cout, int cin, int taps, int rows_pad, int transpose_flip,
                        cudaStream_t st);
 int bn_apply_h(const float* y, void* x, const int32_t* img_frame, const float* scale, const float* shift, int n_img,

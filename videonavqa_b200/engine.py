@@ -300,6 +300,7 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
 
 
 _SIDE = {}
+SIDE_BWD = os.environ.get("VNQA_SIDE_BWD", "0") == "1"
 
 
 def _side_stream(dev):
@@ -328,9 +329,19 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
     gen_done = None
 
     def generator_backward():
-        """FiLM generator backward (+ chained-LSTM BPTT + embedding).  Latency-bound and independent of the remaining
-        convolution backward: runs on the side stream as soon as dfilm is complete (after block 0's FiLM backward)."""
+        """FiLM generator backward (+ chained-LSTM BPTT + embedding), as soon as dfilm is complete (after block 0's
+        FiLM backward).  It is latency-bound (64 CTAs for ~2.4 ms) and independent of the remaining convolution
+        backward, but overlapping it costs more than it hides: the persistent tensor-core kernels use a static tile
+        schedule, so the clusters that find their SMs taken start their whole tile list late (measured at k = 0:
+        dgrad 3.3 -> 6.9 ms, wgrad 3.7 -> 4.7 ms, 1x1 0.43 -> 1.55 ms).  Default: in line on the compute stream;
+        VNQA_SIDE_BWD=1 restores the side-stream overlap."""
         nonlocal gen_done
+        if not SIDE_BWD:
+            with _Nvtx("vnqa.K6.film_generator.bwd"):
+                local = GradSink(None, grads._bucket if isinstance(grads, GradSink) else None)
+                gen_bwd(P, cache, ctx, dfilm, q_input, q_lens32, local)
+            gen_done = (None, local)
+            return
         side.wait_stream(main)
         with torch.cuda.stream(side), _Nvtx("vnqa.K6.film_generator.bwd"):
             local = GradSink(None, grads._bucket if isinstance(grads, GradSink) else None)
@@ -384,7 +395,8 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
     ops.conv_wgrad(dy0, ctx["x0"], dw0, n_img=n_img, cout=C, cin=c_in, taps=9, act=act, grad_unscale=un)
     grads["conv_init.weight"] = dw0
     # ---- join the side stream; its gradients are published (and all-reduced, if a hook is set) from the main stream
-    main.wait_event(gen_done[0])
+    if gen_done[0] is not None:
+        main.wait_event(gen_done[0])
     for n_, t_ in gen_done[1].items():
         grads[n_] = t_
 

@@ -9,8 +9,10 @@ import torch.nn as nn
 
 from .. import engine, ops
 
-# operand storage of the tensor-core kernels when neither VNQA_OPERANDS nor set_operands() says otherwise
-DEFAULT_OPERANDS = "tf32"
+# Operand storage of the tensor-core kernels when neither VNQA_OPERANDS nor set_operands() says otherwise.  fp16 has the
+# same 10-bit mantissa as tf32 and passes the same gates (tests/test_gpu_fp16.py: logits 1.4e-4 from the fp32 reference
+# at the benchmark shape, 100 % argmax agreement over 4096 clips, the same gradient table) at twice the MMA rate.
+DEFAULT_OPERANDS = "fp16"
 
 
 def reference_init(module):
