@@ -48,6 +48,19 @@ try:
     cv2.destroyAllWindows = lambda *a, **k: None
 except Exception:
     pass
+# torch 1.4 (the reference's pin) allowed indexing a CPU tensor with a CUDA index tensor; the test driver does it
+# (eval/q_and_v_test.py:115-117, q_ids is never moved to the GPU).  PyTorch 2 raises - restore the old behaviour.
+import torch
+_getitem = torch.Tensor.__getitem__
+
+
+def _getitem_compat(self, idx):
+    if isinstance(idx, torch.Tensor) and idx.is_cuda and not self.is_cuda:
+        idx = idx.cpu()
+    return _getitem(self, idx)
+
+
+torch.Tensor.__getitem__ = _getitem_compat
 '''
 
 

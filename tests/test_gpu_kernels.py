@@ -12,12 +12,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("binary", ["test_conv_gemm", "test_wgrad"])
-def test_standalone_cuda_harness(binary):
+@pytest.mark.parametrize("binary,args", [
+    ("test_conv_gemm", []),                       # every epilogue, ragged / narrow shapes, naive fp64 CUDA reference
+    ("test_wgrad", ["--perf"]),                   # incl. the CTA-pair kernel at the eval.sh shapes (2240 frame images)
+    ("stress_cluster_share", ["--iters", "1500"]),  # CTA-pair kernels while another stream keeps taking SMs away
+])
+def test_standalone_cuda_harness(binary, args):
     exe = os.path.join(ROOT, "build", binary)
-    if not os.path.exists(exe):
-        pytest.skip("build/%s missing (produced by __graft_entry__.build())" % binary)
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    # built by __graft_entry__.build() and shipped with the snapshot: a GPU box without it is a broken build, not a skip
+    assert os.path.exists(exe), "build/%s is missing: run __graft_entry__.build()" % binary
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 

@@ -23,9 +23,27 @@ __global__ void __launch_bounds__(256) frames_to_nhwc_rows_kernel(const float* _
   const int run = VNQA_IMG_W * Tn;
   const int nc = min(CH, C - cs * CH);   // the last slab may be partial (C is a multiple of 32)
   const float* src = v + (((long long)b * C + cs * CH) * VNQA_IMG_PIX + h * VNQA_IMG_W) * Tn;
-  for (int i = threadIdx.x; i < nc * run; i += blockDim.x) {
-    const int c = i / run, j = i - c * run;
-    Op<T>::st(tile + c * pitch + j, __ldg(src + (long long)c * VNQA_IMG_PIX * Tn + j), 0);
+  // 8 independent loads in flight per thread (the kernel is pure latency otherwise: measured 1.0 TB/s with one);
+  // element i of the slab is (channel i / run, position i % run) - tracked incrementally, no division in the loop
+  {
+    const int total = nc * run;
+    constexpr int U = 8;
+    int c = threadIdx.x / run, j = threadIdx.x - c * run;
+    const int dc = blockDim.x / run, dj = blockDim.x - dc * run;      // one stride of blockDim.x elements
+    for (int i = threadIdx.x; i < total; i += U * blockDim.x) {
+      float val[U];
+      int cc[U], jj[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        cc[u] = c; jj[u] = j;
+        val[u] = (i + u * (int)blockDim.x < total) ? __ldg(src + (long long)c * VNQA_IMG_PIX * Tn + j) : 0.f;
+        c += dc; j += dj;
+        if (j >= run) { j -= run; ++c; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * (int)blockDim.x < total) Op<T>::st(tile + cc[u] * pitch + jj[u], val[u], 0);
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;

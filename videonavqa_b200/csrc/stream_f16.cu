@@ -23,6 +23,10 @@ __device__ __forceinline__ Half8 pack8(const float* f) {
   h.c = __floats2half2_rn(f[4], f[5]); h.d = __floats2half2_rn(f[6], f[7]);
   return h;
 }
+// one 16-byte store (a plain struct assignment is split into four 4-byte stores: 25 % sector efficiency)
+__device__ __forceinline__ void st8(Half8* p, const Half8& h) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&h);
+}
 __device__ __forceinline__ Half8 ldg8(const Half8* p) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
   return *reinterpret_cast<const Half8*>(&u);
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(256) bn_apply_h_kernel(const float4* __restric
     const float4 t0 = __ldg(shift + ((long long)f * C8 + c8) * 2), t1 = __ldg(shift + ((long long)f * C8 + c8) * 2 + 1);
     float o[8] = {fmaf(v0.x, s0.x, t0.x), fmaf(v0.y, s0.y, t0.y), fmaf(v0.z, s0.z, t0.z), fmaf(v0.w, s0.w, t0.w),
                   fmaf(v1.x, s1.x, t1.x), fmaf(v1.y, s1.y, t1.y), fmaf(v1.z, s1.z, t1.z), fmaf(v1.w, s1.w, t1.w)};
-    x[i] = pack8(o);
+    st8(x + i, pack8(o));
   }
 }
 
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(128) film_bwd_h_kernel(const Half8* __restrict
         o[j] = al[j] * d;
       }
       const Half8 h = pack8(o);
-      op[(long long)p * C8] = h;
+      st8(op + (long long)p * C8, h);
       float back[8];
       unpack8(h, back);
 #pragma unroll

@@ -300,7 +300,7 @@ def trunk_forward(P, bn, cache, plan, v_input, q_input, q_lens32, film_h, film_c
 
 
 _SIDE = {}
-SIDE_BWD = os.environ.get("VNQA_SIDE_BWD", "0") == "1"
+SIDE_BWD = os.environ.get("VNQA_SIDE_BWD", "1") == "1"
 
 
 def _side_stream(dev):
@@ -330,11 +330,11 @@ def trunk_backward(P, cache, ctx, dx_last, q_input, q_lens32, grads, gen_bwd=lst
 
     def generator_backward():
         """FiLM generator backward (+ chained-LSTM BPTT + embedding), as soon as dfilm is complete (after block 0's
-        FiLM backward).  It is latency-bound (64 CTAs for ~2.4 ms) and independent of the remaining convolution
-        backward, but overlapping it costs more than it hides: the persistent tensor-core kernels use a static tile
-        schedule, so the clusters that find their SMs taken start their whole tile list late (measured at k = 0:
-        dgrad 3.3 -> 6.9 ms, wgrad 3.7 -> 4.7 ms, 1x1 0.43 -> 1.55 ms).  Default: in line on the compute stream;
-        VNQA_SIDE_BWD=1 restores the side-stream overlap."""
+        FiLM backward).  Latency-bound (64 CTAs for ~2.4 ms) and independent of the remaining convolution backward,
+        so it runs on the side stream.  The overlap is not free - the persistent tensor-core kernels use a static tile
+        schedule, so clusters that find their SMs taken start their tile list late (block 0's dgrad: 3.3 -> up to
+        6.9 ms) - but it still beats running it in line (measured, fp16: 80.1 vs 81.1 ms per step).
+        VNQA_SIDE_BWD=0 runs it in line on the compute stream."""
         nonlocal gen_done
         if not SIDE_BWD:
             with _Nvtx("vnqa.K6.film_generator.bwd"):
