@@ -154,14 +154,23 @@ def summarise_kernels(klass, steps, ms_per_step):
     return out
 
 
-def hbm_roofline(kernels, peaks):
+def load_traffic(operands):
+    """DRAM bytes per launch measured with ncu --set full (profiles/traffic.json), per operand type."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(operands, {})
+    except Exception:
+        return {}
+
+
+def hbm_roofline(kernels, peaks, traffic=None):
     """HBM roofline entry for the FiLM-backward streaming kernel (reads dOut and z, writes dz: 3 activation tensors)."""
     try:
         k = kernels["hbm.film_bwd"]
         peak = float(peaks.get("hbm_gbs") or 6650.0)
         return {"bound": "hbm", "kernel": "film_bwd_kernel (autograd of the FiLM modulation: reads dOut and z, writes dz)",
                 "achieved": k["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": round(k["gb_per_s"] / peak, 4),
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else
+                "traffic": (traffic or {}).get("hbm.film_bwd"),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else
                 "fallback 6.65 TB/s (B200_PROFILING.md)"}
     except Exception:
         return None
@@ -474,11 +483,7 @@ def gpu_leg(args):
     roof = None
     if dom_tag in kernels:
         k = kernels[dom_tag]
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_tag)
-        except Exception:
-            pass
+        traffic = load_traffic(model.precision.name).get(dom_tag)
         roof = {"bound": "tensor",
                 "kernel": f"conv_gemm_kernel<EPI_FILM, 2, {'__half' if fp16 else 'float'}> (conv3x3 1024->1024 + FiLM/ReLU/residual)",
                 "achieved": k["tflops"], "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
@@ -513,7 +518,7 @@ def gpu_leg(args):
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": roof,
-        "roofline_hbm": hbm_roofline(kernels, peaks),
+        "roofline_hbm": hbm_roofline(kernels, peaks, load_traffic(model.precision.name)),
         "kernels": kernels,
     }
     if reducer is not None:
