@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128) film_bwd_h_kernel(const Half8* __restrict
     const Half8* zp = z + (long long)img * VNQA_IMG_PIX * C8 + q;
     const Half8* dp = dout + (long long)img * VNQA_IMG_PIX * C8 + q;
     Half8* op = dz + (long long)img * VNQA_IMG_PIX * C8 + q;
-#pragma unroll 5
+#pragma unroll 2
     for (int p = 0; p < VNQA_IMG_PIX; ++p) {
       float zz[8], dd[8], o[8];
       unpack8(ldg8(zp + (long long)p * C8), zz);
