@@ -15,7 +15,9 @@ run() {
   python - "$O/r02_scale_${tag}.json" <<'PY'
 import json, sys
 try:
-    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    line = [l for l in open(sys.argv[1]).read().splitlines() if l.startswith('{"metric"')][-1]   # NCCL INFO shares stdout
+    d = json.loads(line)
+    open(sys.argv[1].replace(".json", ".line.json"), "w").write(line + "\n")
     print(d["n_gpus"], "GPUs:", d["value"], "clips/s", d["ms_per_step"], "ms | e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "ms | dp_check", d.get("dp_check"), "| bytes", d.get("allreduce_bytes_per_step"), d["clocks"])
 except Exception as e:
     print("no json:", e)
