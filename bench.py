@@ -12,10 +12,12 @@ clip_grad_norm + Adam, exactly the reference's loop body (eval/q_and_v_eval.py:1
 `value`   clips/s with the batch already resident in HBM (CUDA events, max over ranks).
 `e2e`     same metric through the public module API with HOST (pinned) inputs: every step copies that step's
           v_input/q_input/lengths/labels host->device (prefetched on a copy stream) and reads the loss back.
-`roofline` tensor-core roofline of the dominant kernel (conv3x3 + FiLM epilogue, tcgen05 kind::tf32) timed per
-          launch with CUDA events inside the timed region; peak = measured bf16 dense TFLOP/s / 2 (tf32 runs at half
-          the bf16 rate) from MEASURED_PEAKS.json.
-`cpu_baseline` the CPU oracle (port of the reference, oracle/film_oracle.py) on the host cores, bounded sample.
+`roofline` tensor-core roofline of the dominant kernel (conv3x3 + FiLM epilogue, tcgen05 kind::f16 by default,
+          kind::tf32 with --operands tf32) timed per launch with CUDA events inside the timed region; peak = measured
+          bf16 dense TFLOP/s from MEASURED_PEAKS.json (halved for tf32, which runs at half the 16-bit rate).
+`cpu_baseline` the reference's own module (oracle/_ref/reference/models_hot, staged unmodified by oracle/stage_ref.py;
+          kind "reference") on the host cores, bounded sample, in a child process with the GPUs hidden; the oracle
+          restatement (kind "port") only when oracle/_ref is absent.
 --impl reference: only the CPU leg, as its own JSON line.
 """
 import argparse
@@ -52,6 +54,7 @@ def parse():
     ap.add_argument("--ragged", action="store_true", help="ragged v_lens (secondary config) instead of all 35")
     ap.add_argument("--cpu-clips", type=int, default=4, help="clips in the bounded CPU sample (~10 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
                     help="fused = videonavqa_b200.optim.FusedClipAdam over the flat bucket; torch = clip_grad_norm_ + Adam")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager baseline on the same GPU")
@@ -61,33 +64,95 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------- CPU leg
-def cpu_leg(workload, clips, iters=1, warm=0, kind="attn"):
-    """Time the CPU oracle (port of the reference forward/backward) on all host cores, bounded sample."""
+REF_HOT = os.path.join(ROOT, "oracle", "_ref", "reference", "models_hot")
+REF_FILES = {"attn": ("film_attn_pt_stem.py", "FiLMAttnPretrainedStem"),
+             "gp": ("film_global_pooling_pt_stem.py", "FiLMGlobalPoolingPretrainedStem"),
+             "tmh": ("time_multi_hop_pt_stem.py", "TimeMultiHopFiLMPretrainedStem")}
+
+
+def _cpu_worker(kind, workload, clips, iters, warm):
+    """Runs in a child process with the GPUs hidden (the reference picks its CUDA branch from
+    torch.cuda.is_available()).  Times the reference's OWN module (oracle/_ref/reference/models_hot, staged unmodified
+    by oracle/stage_ref.py) when it is there — kind "reference" — else the oracle restatement — kind "port"."""
     import torch
     from oracle import film_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    p = O.init_params(kind, c_in=CFG["c_in"], C=CFG["C"], nb=MODELS[kind]["nb"], hidden=CFG["hidden"],
-                      at_hidden=CFG["at_hidden"], embed=CFG["embed"], vocab=CFG["vocab"], classes=CFG["classes"],
-                      tail=MODELS[kind]["tail"] or 32, T=CFG["T"], seed=1)
     v, q, v_lens, q_lens, labels = O.synthetic_batch(clips, c_in=CFG["c_in"], T=CFG["T"], Lq=CFG["Lq"],
                                                      vocab=CFG["vocab"], classes=CFG["classes"], seed=0)
+    fname, cls = REF_FILES[kind]
+    path = os.path.join(REF_HOT, fname)
+    step = None
+    if os.path.exists(path) and not os.environ.get("BENCH_CPU_PORT"):
+        import importlib.util
+        assert not torch.cuda.is_available(), "the reference CPU arm must run with the GPUs hidden"
+        spec = importlib.util.spec_from_file_location("_vnqa_reference_" + kind, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        kw = dict(batch_size=clips, q_embedding_size=CFG["embed"], nb_classes=CFG["classes"],
+                  num_input_channels=CFG["c_in"], num_res_block_channels=CFG["C"], num_res_blocks=MODELS[kind]["nb"],
+                  hidden_size=CFG["hidden"], vocab_size=CFG["vocab"])
+        if kind == "attn":
+            kw.update(at_hidden_size=CFG["at_hidden"], max_num_frames=CFG["T"], q_encoder="lstm")
+        elif kind == "gp":
+            kw.update(num_tail_channels=MODELS[kind]["tail"], q_encoder="lstm")
+        else:
+            kw.update(num_tail_channels=MODELS[kind]["tail"])
+        torch.manual_seed(1)
+        model = getattr(mod, cls)(**kw)
+        model.apply(model.weights_init)                      # eval/q_and_v_eval.py, as the driver does
+        loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
+        model.train(workload == "train")
+
+        def step():
+            model.init_hidden()
+            if workload == "train":
+                model.zero_grad()
+                loss_fn(model(v, q, v_lens, q_lens), labels).backward()
+            else:
+                with torch.no_grad():
+                    model(v, q, v_lens, q_lens)
+        kind_s, what = "reference", f"the reference's own {cls} (unmodified, CPU branch)"
+    else:
+        p = O.init_params(kind, c_in=CFG["c_in"], C=CFG["C"], nb=MODELS[kind]["nb"], hidden=CFG["hidden"],
+                          at_hidden=CFG["at_hidden"], embed=CFG["embed"], vocab=CFG["vocab"], classes=CFG["classes"],
+                          tail=MODELS[kind]["tail"] or 32, T=CFG["T"], seed=1)
+
+        def step():
+            bn = O.new_bn_state(CFG["C"])
+            st = O.new_film_state(clips, CFG["hidden"])
+            if workload == "train":
+                O.loss_and_grads(kind, p, bn, st, v, q, v_lens, q_lens, labels, training=True)
+            else:
+                with torch.no_grad():
+                    O.FORWARDS[kind](p, bn, st, v, q, v_lens, q_lens, training=False)
+        kind_s, what = "port", "the CPU oracle (restatement of the reference)"
     times = []
     for i in range(warm + iters):
-        bn = O.new_bn_state(CFG["C"])
-        st = O.new_film_state(clips, CFG["hidden"])
         t0 = time.perf_counter()
-        if workload == "train":
-            O.loss_and_grads(kind, p, bn, st, v, q, v_lens, q_lens, labels, training=True)
-        else:
-            with torch.no_grad():
-                O.FORWARDS[kind](p, bn, st, v, q, v_lens, q_lens, training=False)
+        step()
         if i >= warm:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return {"value": clips / sec, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"{clips} full-length clips (35 frames), {workload} step, {iters} timed run(s), "
-                      f"torch CPU fp32 with {cores} threads", "sec_per_step": sec}
+    print("CPU_WORKER " + json.dumps(
+        {"value": clips / sec, "unit": "clips/s", "cores": cores, "kind": kind_s,
+         "sample": f"{what}: {clips} full-length clips (35 frames), {workload} step, {iters} timed run(s), "
+                   f"torch CPU fp32 with {cores} threads", "sec_per_step": sec}))
+
+
+def cpu_leg(workload, clips, iters=1, warm=0, kind="attn"):
+    """CPU baseline: the reference's own implementation of the path (or the oracle port when oracle/_ref is absent) on
+    all host cores, bounded sample, in a child process that cannot see the GPUs."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", "--model", kind, "--workload",
+                        workload, "--cpu-clips", str(clips), "--steps", str(iters), "--warmup", str(warm)],
+                       env=env, capture_output=True, text=True, timeout=1500)
+    for line in r.stdout.splitlines():
+        if line.startswith("CPU_WORKER "):
+            return json.loads(line[len("CPU_WORKER "):])
+    raise RuntimeError("CPU baseline worker failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -538,6 +603,9 @@ def gpu_leg(args):
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
+    if args.cpu_worker:
+        _cpu_worker(args.model, args.workload, args.cpu_clips, args.steps, args.warmup)
+        return
     start_watchdog()
     if args.impl == "reference":
         if rank != 0:
@@ -550,7 +618,7 @@ def main():
                 "warmup": min(args.warmup, 1), "ms_per_step": round(cb["sec_per_step"] * 1e3, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "config": {"workload": workload_name(args),
-                           "sample": f"CPU oracle (port of the reference), each step a bounded sample of "
+                           "sample": f"CPU implementation ({cb['kind']}), each step a bounded sample of "
                                      f"{args.cpu_clips} clips x 35 frames of that workload"},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": round(cb["value"], 4), "unit": "clips/s", "h2d_bytes_per_step": 0,
