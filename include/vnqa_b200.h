@@ -10,8 +10,13 @@
  *
  * Activation layout ("frame-image major NHWC"): a batch of clips is flattened to n_img = sum(v_lens) frame
  * images ordered frame-major (all clips of frame 0, then frame 1, ...; clips sorted by descending length as
- * the reference requires, models/film_attn_pt_stem.py:184-186), each image stored as [10][13][C] fp32.
- * Tensors that feed a tensor-core MMA hold tf32-representable values (rounded to nearest by their producer).
+ * the reference requires, models/film_attn_pt_stem.py:184-186), each image stored as [10][13][C].
+ * Element type of every tensor that feeds a tensor-core MMA (activations, packed weights, backward signals) is chosen
+ * per call by `act_dtype`: VNQA_ACT_FP16 = IEEE half (the default of the Python layer; kind::f16 MMAs) or
+ * VNQA_ACT_TF32 = fp32 words holding tf32-representable values (kind::tf32 MMAs, half the rate).  Both have a 10-bit
+ * mantissa; producers round once, to nearest, when they store.  Accumulation, BatchNorm statistics, the small-GEMM
+ * tail, gradients of parameters and the optimizer are fp32 in either mode.  `void*` operands are such tensors;
+ * `float*` operands are always fp32.
  */
 #ifndef VNQA_B200_H
 #define VNQA_B200_H
@@ -22,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VNQA_ABI_VERSION 2
+#define VNQA_ABI_VERSION 3
 #define VNQA_IMG_H 10
 #define VNQA_IMG_W 13
 #define VNQA_IMG_PIX 130 /* hard-coded 130 = 10*13 in models/film_attn_pt_stem.py:56 */
@@ -68,7 +73,10 @@ enum {
   VNQA_EPI_FILM = 3,             /* z = acc + bias; out = relu(a*z + b) + res    ResBlock body (:224-241) */
   VNQA_EPI_PARTIAL = 4,          /* out[split][row][co] = acc                    split-K GEMM (fc_embed_attn :244) */
   VNQA_EPI_DGRAD_RES = 5,        /* out = (acc + add) * [mask > 0]               dX of conv3x3 + skip, through ReLU (:219) */
-  VNQA_EPI_PLAIN = 7             /* out = acc                                    dX of conv1x1 / Linear */
+  VNQA_EPI_PLAIN = 7,            /* out = acc                                    dX of conv1x1 / Linear */
+  VNQA_EPI_BIAS = 8,             /* out = acc + bias                             frozen stem conv11/21/31 (obj_detector.py:71,76,81) */
+  VNQA_EPI_BIAS_AFFINE_RELU = 9  /* out = [maxpool2x2] relu((acc + bias) * scale + shift)   stem conv12/22/32 + BN eval + ReLU
+                                    [+ pool] (obj_detector.py:71-84) */
 };
 
 /* Operand / activation storage of the tensor-core kernels ("act" below): tf32 = fp32 storage holding tf32-representable
@@ -80,13 +88,13 @@ enum { VNQA_ACT_TF32 = 0, VNQA_ACT_FP16 = 1 };
 typedef struct {
   /* operands ("act" = float or __half, see act_dtype) */
   const void* w_packed;  /* act [taps][rows_pad][cin] from vnqa_pack_conv_weight (flat: [rows_pad][cin*splits]) */
-  const void* x;         /* act activations [n_img][130][cin] (conv) or [n_img][x_ld] (flat) */
+  const void* x;         /* act activations [n_img][img_h*img_w][cin] (conv) or [n_img][x_ld] (flat) */
   int32_t taps;          /* 1 or 9 */
   int32_t cin;           /* reduction length per tap (per split when flat); tf32: multiple of 32, fp16: of 8 */
   int32_t cout;          /* real output channels */
   int32_t rows_pad;      /* cout rounded up to 128 */
   int32_t n_img;         /* conv: images; flat: rows of x */
-  int32_t flat;          /* 0: conv over 10x13 images; 1: plain GEMM */
+  int32_t flat;          /* 0: conv over img_h x img_w images (10 x 13 by default); 1: plain GEMM */
   int32_t x_ld;          /* flat only: row stride of x in elements (>= cin*splits) */
   int32_t splits;        /* flat only: split-K factor */
   int32_t epi;
@@ -110,9 +118,25 @@ typedef struct {
   int32_t act_dtype;     /* VNQA_ACT_TF32 / VNQA_ACT_FP16 */
   int32_t out_f32;       /* fp16 only, BIAS_RELU / PLAIN: store fp32 (tensors that leave the fp16 domain) */
   float grad_unscale;    /* 0 is read as 1 */
+  /* image geometry of the conv (flat == 0); 0 = the FiLM trunk's 10 x 13.  img_w must be 13, 26 or 52 (a 208-pixel
+   * tile is then (8, 4, 2) images x 2 rows x img_w), img_h even: the frozen stem's 40 x 52 / 20 x 26 / 10 x 13 maps */
+  int32_t img_h;
+  int32_t img_w;
+  int32_t pool;          /* BIAS_AFFINE_RELU, img_w 26 / 52: write the 2x2 max-pooled map [n_img][img_h/2 * img_w/2][cout] */
 } vnqa_conv_args;
 
 int vnqa_conv_gemm(const vnqa_conv_args* args, void* stream);
+
+/* ---- frozen stem (models/obj_detector.py:69-86, run under no_grad in eval mode by
+ * eval/q_and_v_eval.py:104-110).  Its six 3x3 convolutions are vnqa_conv_gemm with img_h / img_w / pool and the BIAS /
+ * BIAS_AFFINE_RELU epilogues; these two calls are the layout changes at its ends.
+ * x (n_img, C, P) fp32 NCHW -> out [n_img][P][C] act, out = x * scale[c] + shift[c] (bn_input in eval mode, :70;
+ * scale == shift == NULL: plain relayout). */
+int vnqa_nchw_to_nhwc_affine(const float* x, void* out, const float* scale, const float* shift, int32_t n_img,
+                             int32_t C, int32_t P, int32_t act_dtype, void* stream);
+/* x [n_img][P][C] (fp32, or half when x_half != 0) -> out (n_img, C, P) fp32 NCHW, the layout the reference's callers
+ * stack per frame (q_and_v_eval.py:110) */
+int vnqa_nhwc_to_nchw(const void* x, float* out, int32_t n_img, int32_t C, int32_t P, int32_t x_half, void* stream);
 
 /* ---- K4: weight gradient dW[co][ci][tap] = grad_unscale * sum_rows dY[row][co] * X[row (+) tap][ci] on tcgen05
  * (MN-major operands of type act_dtype, split-K over pixels, DETERMINISTIC turn-ordered fp32 reduction: two launches on

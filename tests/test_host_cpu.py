@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), f"libvnqa_b200.so does not export {s}"
     assert sorted(_lib.SIGNATURES) == syms, set(_lib.SIGNATURES) ^ set(syms)
-    assert handle.vnqa_abi_version() == 2
+    assert handle.vnqa_abi_version() == 3
 
 
 def test_conv_args_struct_matches_header_field_order():

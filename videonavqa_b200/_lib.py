@@ -30,11 +30,13 @@ class ConvArgs(ctypes.Structure):
         ("film", c_void_p), ("film_row", c_void_p), ("film_ld", c_int32), ("alpha_off", c_int32),
         ("res", c_void_p), ("z_out", c_void_p), ("add", c_void_p), ("dbias", c_void_p),
         ("act_dtype", c_int32), ("out_f32", c_int32), ("grad_unscale", c_float),
+        ("img_h", c_int32), ("img_w", c_int32), ("pool", c_int32),
     ]
 
 
 EPI_BIAS_RELU, EPI_BIAS_RELU_AFFINE, EPI_BIAS_RELU_STATS, EPI_FILM, EPI_PARTIAL, EPI_DGRAD_RES = 0, 1, 2, 3, 4, 5
 EPI_PLAIN = 7
+EPI_BIAS, EPI_BIAS_AFFINE_RELU = 8, 9      # frozen stem (models/obj_detector.py)
 ACT_TF32, ACT_FP16 = 0, 1
 
 P, I32, I64, F32 = c_void_p, c_int32, c_int64, c_float
@@ -52,6 +54,8 @@ SIGNATURES = {
     "vnqa_to_half": [P, P, I64, F32, P],
     "vnqa_permute_fc_weight": [P, P, I32, I32, I32, I32, P],
     "vnqa_conv_gemm": [POINTER(ConvArgs), P],
+    "vnqa_nchw_to_nhwc_affine": [P, P, P, P, I32, I32, I32, I32, P],
+    "vnqa_nhwc_to_nchw": [P, P, I32, I32, I32, I32, P],
     "vnqa_conv_wgrad_ws_bytes": [I32, I32, I32, POINTER(c_int64)],
     "vnqa_conv_wgrad": [P, P, P, P, I32, I32, I32, I32, I32, I32, F32, P],
     "vnqa_sgemm": [P, P, P, P, I32, I32, I32, I64, I64, I64, I64, I64, I32, I32, I32, P],
@@ -111,7 +115,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)  # AttributeError if the library does not export a declared symbol
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, c_int32)
-        if handle.vnqa_abi_version() != 2:
+        if handle.vnqa_abi_version() != 3:
             raise VnqaError("libvnqa_b200.so ABI version mismatch")
         _lib = handle
     return _lib

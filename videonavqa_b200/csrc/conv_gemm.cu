@@ -55,7 +55,10 @@ struct Cfg {
 
 struct KParams {
   int taps, k_chunks, m_tiles, n_tiles, splits, rows_pad, flat, cout, n_img, no_round;
-  int out_f32;                 // fp16 operands only: BIAS_RELU / PLAIN store fp32 (tensors that leave the fp16 domain)
+  int out_f32;                 // fp16 operands only: BIAS_RELU / PLAIN / BIAS_AFFINE_RELU store fp32 (tensors that leave the fp16 domain)
+  // image geometry (conv): W = 13 << g_shift, H = 2 * rp; a tile is (8 >> g_shift) images x 2 rows x W = 208 pixels,
+  // i.e. 8 groups of 26 consecutive output rows, (1 << g_shift) groups per image
+  int rp, g_shift, hw, w2, pool;
   long long out_split_stride;  // PARTIAL: n_img * cout
   void* out;
   const float* bias;
@@ -101,10 +104,10 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord&
   const bool co_ok = co < p.cout;
   float bias = 0.f, scale = 1.f, shift = 0.f;
   if (EPI == VNQA_EPI_BIAS_RELU || EPI == VNQA_EPI_BIAS_RELU_AFFINE || EPI == VNQA_EPI_BIAS_RELU_STATS ||
-      EPI == VNQA_EPI_FILM) {
+      EPI == VNQA_EPI_FILM || EPI == VNQA_EPI_BIAS || EPI == VNQA_EPI_BIAS_AFFINE_RELU) {
     if (co_ok) bias = __ldg(p.bias + co);
   }
-  if (EPI == VNQA_EPI_BIAS_RELU_AFFINE && co_ok) {
+  if ((EPI == VNQA_EPI_BIAS_RELU_AFFINE || EPI == VNQA_EPI_BIAS_AFFINE_RELU) && co_ok) {
     scale = __ldg(p.scale + co);
     shift = __ldg(p.shift + co);
   }
@@ -113,6 +116,40 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord&
   float* out_f = reinterpret_cast<float*>(p.out);
   if (EPI == VNQA_EPI_PARTIAL) out_f += (long long)tc.sp * p.out_split_stride;
   const bool f32_out = O::HALF && p.out_f32;    // fp16 path only; the tf32 path stores fp32 through out_t anyway
+
+  if (EPI == VNQA_EPI_BIAS_AFFINE_RELU && p.pool) {
+    // 2x2 max-pool fused behind BatchNorm(eval) + ReLU: a tile holds both rows of a row pair, so every pooling window
+    // lies inside one thread's accumulator columns.  Unit = 26 columns of the upper row + the 26 below them.
+    const int g = 1 << p.g_shift, half_g = g >> 1;
+    const int wo2 = p.w2 >> 2;                       // pooled row length W / 2
+#pragma unroll 1
+    for (int nl = 0; nl < IMG_PER_TILE; ++nl) {
+      if ((nl & (g - 1)) >= half_g) continue;        // lower-row groups are consumed with their upper partner
+      uint32_t va[ROWS_PER_IMG_TILE], vb[ROWS_PER_IMG_TILE];
+      const uint32_t ca = t_base + nl * ROWS_PER_IMG_TILE, cb = ca + half_g * ROWS_PER_IMG_TILE;
+      tmem_ld_x16(ca, va); tmem_ld_x8(ca + 16, va + 16); tmem_ld_x2(ca + 24, va + 24);
+      tmem_ld_x16(cb, vb); tmem_ld_x8(cb + 16, vb + 16); tmem_ld_x2(cb + 24, vb + 24);
+      tmem_ld_wait();
+      const int img = (tc.nt / p.rp) * (IMG_PER_TILE >> p.g_shift) + (nl >> p.g_shift);
+      if (img < p.n_img && co_ok) {
+        const long long prow0 = (long long)img * (p.hw >> 2) + (tc.nt % p.rp) * wo2 + (nl & (g - 1)) * 13;
+        const long long o0 = prow0 * p.cout + co;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+          // relu and max commute; the affine does not (scale may be negative), so it is applied to all four
+          const float y0 = fmaf(__uint_as_float(va[2 * j]) + bias, scale, shift);
+          const float y1 = fmaf(__uint_as_float(va[2 * j + 1]) + bias, scale, shift);
+          const float y2 = fmaf(__uint_as_float(vb[2 * j]) + bias, scale, shift);
+          const float y3 = fmaf(__uint_as_float(vb[2 * j + 1]) + bias, scale, shift);
+          const float y = fmaxf(fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)), 0.f);
+          if (f32_out) out_f[o0 + j * (long long)p.cout] = y;
+          else O::st(out_t + o0 + j * (long long)p.cout, y, p.no_round);
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
 
   double st_sum = 0.0, st_sq = 0.0;  // STATS: running per-frame accumulators
   int st_frame = -1;
@@ -134,8 +171,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord&
       long long rem = (long long)p.n_img - row0;
       nvalid = rem >= ROWS_PER_IMG_TILE ? ROWS_PER_IMG_TILE : (rem > 0 ? (int)rem : 0);
     } else {
-      img = (tc.nt / 5) * IMG_PER_TILE + nl;
-      row0 = (long long)img * VNQA_IMG_PIX + (tc.nt % 5) * ROWS_PER_IMG_TILE;
+      img = (tc.nt / p.rp) * (IMG_PER_TILE >> p.g_shift) + (nl >> p.g_shift);
+      row0 = (long long)img * p.hw + (tc.nt % p.rp) * p.w2 + (nl & ((1 << p.g_shift) - 1)) * ROWS_PER_IMG_TILE;
       nvalid = img < p.n_img ? ROWS_PER_IMG_TILE : 0;
     }
     if (nvalid > 0 && co_ok) {
@@ -147,6 +184,18 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, const TileCoord&
         for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
           if (r < nvalid) {
             const float y = fmaxf(__uint_as_float(v[r]) + bias, 0.f);
+            if (f32_out) out_f[o0 + r * ld] = y;
+            else O::st(out_t + o0 + r * ld, y, p.no_round);
+          }
+      } else if (EPI == VNQA_EPI_BIAS) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) O::st(out_t + o0 + r * ld, __uint_as_float(v[r]) + bias, p.no_round);
+      } else if (EPI == VNQA_EPI_BIAS_AFFINE_RELU) {
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_IMG_TILE; ++r)
+          if (r < nvalid) {
+            const float y = fmaxf(fmaf(__uint_as_float(v[r]) + bias, scale, shift), 0.f);
             if (f32_out) out_f[o0 + r * ld] = y;
             else O::st(out_t + o0 + r * ld, y, p.no_round);
           }
@@ -296,7 +345,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.flat) {
         b1 = tc.nt * BN + rank * C::B_ROWS; b2 = 0; b3 = 0;
       } else {
-        b1 = 0; b2 = (tc.nt % 5) * 2; b3 = (tc.nt / 5) * IMG_PER_TILE + rank * (IMG_PER_TILE / NCTA);
+        const int ipt = IMG_PER_TILE >> p.g_shift;   // images per tile: 8 / 4 / 2
+        b1 = 0; b2 = (tc.nt % p.rp) * 2; b3 = (tc.nt / p.rp) * ipt + rank * (ipt / NCTA);
       }
       const int k_base = tc.sp * p.k_chunks * BK;
       for (int tap = 0; tap < p.taps; ++tap) {
@@ -450,14 +500,32 @@ static int conv_gemm_typed(const vnqa_conv_args* a, cudaStream_t st) {
   const int splits = a->flat ? (a->splits > 0 ? a->splits : 1) : 1;
   VNQA_REQUIRE(splits == 1 || a->cin % BK == 0, "vnqa_conv_gemm: split-K needs cin per split to be a multiple of %d", BK);
   VNQA_REQUIRE(O::HALF || a->cin % BK == 0, "vnqa_conv_gemm: cin must be a multiple of %d (got %d)", BK, a->cin);
-  VNQA_REQUIRE(!a->out_f32 || (O::HALF && (a->epi == VNQA_EPI_BIAS_RELU || a->epi == VNQA_EPI_PLAIN)),
-               "vnqa_conv_gemm: out_f32 is available for fp16 operands with BIAS_RELU and PLAIN");
+  VNQA_REQUIRE(!a->out_f32 || (O::HALF && (a->epi == VNQA_EPI_BIAS_RELU || a->epi == VNQA_EPI_PLAIN ||
+                                           a->epi == VNQA_EPI_BIAS_AFFINE_RELU)),
+               "vnqa_conv_gemm: out_f32 is available for fp16 operands with BIAS_RELU, PLAIN and BIAS_AFFINE_RELU");
+
+  // image geometry: 10 x 13 (the FiLM trunk) unless the caller names one of the frozen stem's (models/obj_detector.py:
+  // 40 x 52 and 20 x 26): W = 13 * 2^s keeps the tile at 208 pixels = (8 >> s) images x 2 rows x W
+  const int img_h = a->img_h > 0 ? a->img_h : VNQA_IMG_H;
+  const int img_w = a->img_w > 0 ? a->img_w : VNQA_IMG_W;
+  int g_shift = 0;
+  if (!a->flat) {
+    VNQA_REQUIRE(img_w == 13 || img_w == 26 || img_w == 52, "vnqa_conv_gemm: img_w must be 13, 26 or 52 (got %d)", img_w);
+    VNQA_REQUIRE(img_h >= 2 && img_h % 2 == 0, "vnqa_conv_gemm: img_h must be even (got %d)", img_h);
+    g_shift = img_w == 13 ? 0 : (img_w == 26 ? 1 : 2);
+    VNQA_REQUIRE(!a->pool || (a->epi == VNQA_EPI_BIAS_AFFINE_RELU && g_shift > 0),
+                 "vnqa_conv_gemm: pool needs BIAS_AFFINE_RELU and img_w 26 or 52");
+  } else {
+    VNQA_REQUIRE(!a->pool, "vnqa_conv_gemm: pool on a flat GEMM");
+  }
+  const int ipt = IMG_PER_TILE >> g_shift;
 
   KParams kp{};
   kp.taps = a->taps;
   kp.k_chunks = (a->cin + BK - 1) / BK;
   kp.m_tiles = a->rows_pad / BM;
-  kp.n_tiles = a->flat ? (a->n_img + BN - 1) / BN : ((a->n_img + IMG_PER_TILE - 1) / IMG_PER_TILE) * 5;
+  kp.rp = img_h / 2; kp.g_shift = g_shift; kp.hw = img_h * img_w; kp.w2 = 2 * img_w; kp.pool = a->pool;
+  kp.n_tiles = a->flat ? (a->n_img + BN - 1) / BN : ((a->n_img + ipt - 1) / ipt) * kp.rp;
   kp.splits = splits;
   kp.rows_pad = a->rows_pad;
   kp.flat = a->flat;
@@ -495,9 +563,9 @@ static int conv_gemm_typed(const vnqa_conv_args* a, cudaStream_t st) {
     if (make_tmap(&tmB, a->x, O::HALF, 4, dims, strides, box)) return -3;
   } else {
     const uint64_t c = (uint64_t)a->cin;
-    const uint64_t dims[4] = {c, VNQA_IMG_W, VNQA_IMG_H, (uint64_t)a->n_img};
-    const uint64_t strides[3] = {c * ES, c * ES * VNQA_IMG_W, c * ES * VNQA_IMG_PIX};
-    const uint32_t box[4] = {BK, VNQA_IMG_W, 2, (uint32_t)(IMG_PER_TILE / ncta)};
+    const uint64_t dims[4] = {c, (uint64_t)img_w, (uint64_t)img_h, (uint64_t)a->n_img};
+    const uint64_t strides[3] = {c * ES, c * ES * img_w, c * ES * img_w * img_h};
+    const uint32_t box[4] = {BK, (uint32_t)img_w, 2, (uint32_t)(ipt / ncta)};
     if (make_tmap(&tmB, a->x, O::HALF, 4, dims, strides, box)) return -3;
   }
 
@@ -524,6 +592,12 @@ static int conv_gemm_typed(const vnqa_conv_args* a, cudaStream_t st) {
     case VNQA_EPI_DGRAD_RES:
       VNQA_REQUIRE(!a->flat && a->add && a->res, "conv_gemm: DGRAD_RES operands");
       return launch_any<VNQA_EPI_DGRAD_RES, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_BIAS:
+      VNQA_REQUIRE(a->bias, "conv_gemm: BIAS needs bias");
+      return launch_any<VNQA_EPI_BIAS, T>(ncta, tmA, tmB, kp, sms, st);
+    case VNQA_EPI_BIAS_AFFINE_RELU:
+      VNQA_REQUIRE(!a->flat && a->bias && a->scale && a->shift, "conv_gemm: BIAS_AFFINE_RELU needs bias/scale/shift");
+      return launch_any<VNQA_EPI_BIAS_AFFINE_RELU, T>(ncta, tmA, tmB, kp, sms, st);
     default:
       set_error("vnqa_conv_gemm: unknown epilogue %d", a->epi);
       return -1;

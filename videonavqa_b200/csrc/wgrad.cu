@@ -18,16 +18,18 @@
 //     tile - each CTA stages its own 128 output channels of dY and its own 128 input channels of X, halving the
 //     operand bytes per MMA flop with respect to the single-CTA 128 x 128 tile;
 //   NCTA = 1: 128 x 128 tiles (small / odd channel counts, the Linear of :244).
-// Split-K over pixel chunks only as far as needed to fill the SMs (about two rounds of tiles per CTA group), in
-// SPLIT-MAJOR tile order: the co-resident CTAs always stream the same pixel range, so dY / X are read from DRAM about
-// once per round instead of once per tile.
+// Split-K over pixel chunks: as many splits as fill the SMs (about two rounds of tiles per CTA group) and at least
+// enough to keep one accumulation chain <= 29120 pixel rows (the tensor core's fp32 accumulation truncates, so its
+// bias grows with the chain length), at most 16.  SPLIT-MAJOR tile order: the co-resident CTAs always stream the same
+// pixel range, so dY / X are read from DRAM about once per round instead of once per tile.
 //
 // DETERMINISTIC reduction of the split-K partial tiles: every (tile, CTA, epilogue warp) owns a turn counter; split s
 // of a tile waits until the counter reads s, then accumulates its partial into the [tap][Cout][Cin] buffer with plain
 // loads/stores (split 0 stores, so the buffer needs no zero-fill) and passes the turn on.  Items are issued in
-// split-major order, so a predecessor is always an earlier item of the static schedule: the wait cannot dead-lock and
-// is almost always already satisfied (the predecessor ran ~2 tile rounds earlier).  The order of the fp32 additions
-// is therefore fixed: two launches on the same operands give the same bits.  (Round 1 used red.global.add.)
+// split-major order, so a predecessor is always an earlier item of the static schedule (owned by a CTA that is
+// resident - the grid is persistent and never exceeds the SM count): the wait cannot dead-lock, and with <= 16 splits
+// the predecessor's epilogue has usually retired by the time the successor's main loop ends.  The order of the fp32
+// additions is therefore fixed: two launches on the same operands give the same bits.  (Round 1 used red.global.add.)
 // The partial tile is transposed through shared memory so that every warp access hits 128 contiguous bytes; a final
 // pass writes PyTorch's (Cout, Cin, kh, kw).
 #include <cstdlib>

@@ -131,10 +131,13 @@ def permute_fc_weight(w, C, inverse=False, n_pad=None, out=None):
 def conv_gemm(w_packed, x, *, taps, cin, cout, n_img, epi, out, flat=False, x_ld=0, splits=1, no_round=False,
               bias=None, scale=None, shift=None, img_frame=None, stat_sum=None, stat_sq=None, film=None,
               film_row=None, film_ld=0, alpha_off=0, res=None, z_out=None, add=None, dbias=None, act=0, out_f32=False,
-              grad_unscale=1.0):
+              grad_unscale=1.0, img_hw=None, pool=False):
+    """img_hw: (H, W) of the conv's images, None = the trunk's 10 x 13 (the frozen stem passes 40 x 52 / 20 x 26)."""
     assert x.dtype == act_dtype(act) and w_packed.dtype == act_dtype(act), (x.dtype, w_packed.dtype, act)
     a = ConvArgs()
     a.act_dtype, a.out_f32, a.grad_unscale = act, int(out_f32), float(grad_unscale)
+    a.img_h, a.img_w = img_hw if img_hw is not None else (0, 0)
+    a.pool = int(pool)
     a.w_packed = w_packed.data_ptr()
     a.x = x.data_ptr()
     a.taps, a.cin, a.cout, a.rows_pad, a.n_img = taps, cin, cout, round_up(cout, 128), n_img
@@ -145,10 +148,36 @@ def conv_gemm(w_packed, x, *, taps, cin, cout, n_img, epi, out, flat=False, x_ld
                     ("res", res), ("z_out", z_out), ("add", add), ("dbias", dbias)):
         setattr(a, name, t.data_ptr() if t is not None else None)
     a.film_ld, a.alpha_off = film_ld, alpha_off
-    rows = n_img if flat else n_img * IMG_PIX
+    rows = n_img if flat else n_img * (IMG_PIX if img_hw is None else img_hw[0] * img_hw[1])
     tag = f"conv_gemm.{'flat' if flat else str(taps) + 'tap'}.epi{epi}.k{cin * splits}.n{cout}"
+    if img_hw is not None:
+        tag += f".{img_hw[0]}x{img_hw[1]}"
     with _timed(tag, 2.0 * rows * cout * cin * splits * taps):
         check(_lib.lib().vnqa_conv_gemm(ctypes.byref(a), _stream()), "conv_gemm")
+    return out
+
+
+def nchw_to_nhwc_affine(x, scale=None, shift=None, act=0, out=None):
+    """x (N, C, H, W) fp32 -> [N][H*W][C] in the operand type, times scale[c] plus shift[c] (csrc/stem.cu)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    N, C, H, W = x.shape
+    if out is None:
+        out = torch.empty(N, H * W, C, device=x.device, dtype=act_dtype(act))
+    with _timed("hbm.stem_in", x.numel() * 4 + out.numel() * out.element_size()):
+        check(_lib.lib().vnqa_nchw_to_nhwc_affine(_p(x), _p(out), _p(scale), _p(shift), N, C, H * W, act, _stream()),
+              "nchw_to_nhwc_affine")
+    return out
+
+
+def nhwc_to_nchw(x, hw, out=None):
+    """x [N][H*W][C] (fp32 or half) -> (N, C, H, W) fp32."""
+    assert x.is_contiguous() and x.dim() == 3 and x.dtype in (torch.float32, torch.float16)
+    N, P, C = x.shape
+    assert P == hw[0] * hw[1]
+    if out is None:
+        out = torch.empty(N, C, hw[0], hw[1], device=x.device, dtype=torch.float32)
+    check(_lib.lib().vnqa_nhwc_to_nchw(_p(x), _p(out), N, C, P, int(x.dtype == torch.float16), _stream()),
+          "nhwc_to_nchw")
     return out
 
 
