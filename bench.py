@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", choices=["train", "eval"], default="train")
+    ap.add_argument("--workload", choices=["train", "eval", "stem"], default="train",
+                    help="train / eval = the FiLM path (headline); stem = the frozen ObjDetectCNN in front of it "
+                         "(SURVEY 8(f) rank 2), 35 per-frame calls per step as the drivers issue them")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--model", choices=list(MODELS), default="attn", help="attn = the headline metric")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU")
@@ -80,6 +82,8 @@ def _cpu_worker(kind, workload, clips, iters, warm):
     torch.set_num_threads(cores)
     v, q, v_lens, q_lens, labels = O.synthetic_batch(clips, c_in=CFG["c_in"], T=CFG["T"], Lq=CFG["Lq"],
                                                      vocab=CFG["vocab"], classes=CFG["classes"], seed=0)
+    if workload == "stem":
+        return _cpu_worker_stem(clips, iters, warm, cores)
     fname, cls = REF_FILES[kind]
     path = os.path.join(REF_HOT, fname)
     step = None
@@ -137,6 +141,46 @@ def _cpu_worker(kind, workload, clips, iters, warm):
     print("CPU_WORKER " + json.dumps(
         {"value": clips / sec, "unit": "clips/s", "cores": cores, "kind": kind_s,
          "sample": f"{what}: {clips} full-length clips (35 frames), {workload} step, {iters} timed run(s), "
+                   f"torch CPU fp32 with {cores} threads", "sec_per_step": sec}))
+
+
+STEM_REF = os.path.join(ROOT, "oracle", "_ref", "reference", "models", "obj_detector.py")
+
+
+def _load_reference_stem():
+    """The reference's own ObjDetectCNN (staged unmodified by oracle/stage_ref.py), built as eval/utils.py:42-51 does."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_vnqa_reference_stem", STEM_REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.ObjDetectCNN(nb_classes=27, num_filters=512, tail_hidden_dim=1024, tail_dropout_p=0, logits=True,
+                            pretrained_features=True).eval()
+
+
+def _cpu_worker_stem(frames, iters, warm, cores):
+    """CPU baseline of the frozen stem: `frames` frame images (one call) through the reference's module (kind
+    "reference") or the oracle restatement (kind "port"); reported in clips/s at 35 frames per clip."""
+    import torch
+    from oracle import stem_oracle as S
+    torch.manual_seed(1)
+    x = torch.randn(frames, 128, 40, 52).clamp_min_(0)
+    if os.path.exists(STEM_REF) and not os.environ.get("BENCH_CPU_PORT"):
+        m = _load_reference_stem()
+        fn, kind_s, what = (lambda: m(x)), "reference", "the reference's own ObjDetectCNN (unmodified)"
+    else:
+        P, _ = S.synthetic_stem_case(1, 8, 52, 512, 1)
+        fn, kind_s, what = (lambda: S.stem_forward(P, x)), "port", "the CPU oracle (restatement of the reference)"
+    times = []
+    with torch.no_grad():
+        for i in range(warm + iters):
+            t0 = time.perf_counter()
+            fn()
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    print("CPU_WORKER " + json.dumps(
+        {"value": frames / CFG["T"] / sec, "unit": "clips/s", "cores": cores, "kind": kind_s,
+         "sample": f"{what}: one call on {frames} frame images of 128x40x52 (= {frames}/35 clip), {iters} timed run(s), "
                    f"torch CPU fp32 with {cores} threads", "sec_per_step": sec}))
 
 
@@ -251,6 +295,8 @@ def _log(msg):
 
 
 def metric_name(args):
+    if args.workload == "stem":
+        return "video-QA clips/sec (frozen stem ObjDetectCNN, 35 frames/clip)"
     mname = {"attn": "FiLM-attn", "gp": "FiLM-gp", "tmh": "time-multi-hop"}[args.model]
     return f"video-QA clips/sec ({mname} fwd+bwd)" if args.workload == "train" \
         else f"video-QA clips/sec ({mname} eval forward)"
@@ -258,6 +304,9 @@ def metric_name(args):
 
 def workload_name(args):
     """The same string on both arms (b200 and reference): the configuration BASELINE.json's metric is quoted on."""
+    if args.workload == "stem":
+        return (f"frozen stem (models/obj_detector.py, 512 filters, eval mode): {args.batch} clips/GPU x 35 frames, one call "
+                f"per frame on ({args.batch}, 128, 40, 52) -> ({args.batch}, 512, 10, 13), as eval/q_and_v_eval.py:104-110")
     M = MODELS[args.model]
     return (f"{M['name']} {args.workload} step, eval.sh hyper-parameters (C_in 512, C 1024, {M['nb']} blocks, hidden 128, "
             f"70 classes), {args.batch} clips/GPU x 35 frames x 512x10x13"
@@ -306,6 +355,187 @@ def eager_gpu_leg(dev, B, steps=2):
                 step()
             e1.record()
             torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {"ms_per_step": round(ms, 2), "clips_per_s": round(B / ms * 1e3, 2)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    return out
+
+
+def stem_leg(args):
+    """the frozen stem in front of the FiLM path.  One step = the drivers' per-batch loop
+    (q_and_v_eval.py:104-110): 35 calls, each on the (B, 128, 40, 52) maps of one frame of every clip."""
+    import torch
+    from videonavqa_b200 import ops
+    from videonavqa_b200.models import ObjDetectCNN
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, T = args.batch, CFG["T"]
+    torch.manual_seed(1)
+    m = ObjDetectCNN(nb_classes=27, num_filters=512, tail_hidden_dim=1024, tail_dropout_p=0, logits=True,
+                     pretrained_features=True).to(dev).eval()
+    if args.operands:
+        m.set_operands(args.operands)
+    with torch.no_grad():                      # trained-looking statistics instead of the identity BatchNorms
+        for bn in (m.bn_input, m.bn1, m.bn2, m.bn3):
+            bn.weight.normal_(0.8, 0.3); bn.bias.normal_(0, 0.3)
+            bn.running_mean.normal_(0, 0.4); bn.running_var.uniform_(0.5, 2.0)
+    m._weight_cache.invalidate()
+    NBUF = 4                                    # distinct per-frame inputs, cycled (4 x 68 MB pinned)
+    host = [torch.randn(B, 128, 40, 52).clamp_min_(0).pin_memory() for _ in range(NBUF)]
+    dev_in = [h.to(dev) for h in host]
+    h2d = T * host[0].numel() * 4
+
+    def step(fetch):
+        y = None
+        for j in range(T):
+            y = m(fetch(j))
+        return y
+
+    resident = lambda j: dev_in[j % NBUF]      # noqa: E731
+    for _ in range(args.warmup):
+        step(resident)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ops.PROFILE = []
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(resident)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (ops.LAUNCHES - l0) // args.steps
+    prof, ops.PROFILE = ops.PROFILE, None
+    sampler.stop()
+    klass = {}
+    for tag, flops, a, b in prof:
+        d = klass.setdefault(tag, [0.0, 0, flops, []])
+        t = a.elapsed_time(b)
+        d[0] += t; d[1] += 1; d[3].append(t)
+    kernels = summarise_kernels(klass, args.steps, ms)
+
+    # end to end: every call's input comes from pinned host memory through a double buffer on a copy stream; the
+    # features of the last frame are reduced to one number that is read back every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [torch.empty_like(dev_in[0]) for _ in range(2)]
+    free = [None, None]
+    cnt = [0]
+
+    def prefetch(k):
+        if free[k % 2] is not None:
+            copy_stream.wait_event(free[k % 2])
+        with torch.cuda.stream(copy_stream):
+            slots[k % 2].copy_(host[k % NBUF], non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        return ev
+
+    def e2e_step():
+        k0 = cnt[0]
+        ev = prefetch(k0)
+        y = None
+        for j in range(T):
+            k = k0 + j
+            torch.cuda.current_stream().wait_event(ev)
+            if j + 1 < T:
+                ev = prefetch(k + 1)
+            y = m(slots[k % 2])
+            done = torch.cuda.Event(); done.record(torch.cuda.current_stream())
+            free[k % 2] = done
+        cnt[0] += T
+        return float(y.sum().item())
+
+    e2e_step()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_ms = f0.elapsed_time(f1) / args.steps
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fp16 = m.precision.fp16
+    peak = (peaks.get("bf16_tflops_sustained") or 1400.0) * (1.0 if fp16 else 0.5)
+    dom = max((t for t in klass if t.startswith("conv_gemm")), key=lambda t: klass[t][0])
+    k = kernels[dom]
+    gflop_frame = 2 * 9 * (2080 * 128 * 512 + 2080 * 512 * 512 + 2 * 520 * 512 * 512 + 2 * 130 * 512 * 512) * 1e-9
+    out = {
+        "metric": metric_name(args), "value": round(B / (ms * 1e-3), 2), "unit": "clips/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 operands, fp32 accumulate" if fp16 else "tf32 operands, fp32 accumulate", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frames_per_step": B * T, "gflop_per_frame": round(gflop_frame, 3),
+                   "l2": "inputs larger than L2 (68 MB per call in, 136 MB intermediates)"},
+        "frames_per_s": round(B * T / (ms * 1e-3), 1),
+        "model_tflops": round(B * T * gflop_frame / ms, 1),
+        "e2e": {"value": round(B / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
+                "how": "each call's (B,128,40,52) input copied from pinned host memory through a double buffer on a "
+                       "copy stream; one checksum of the features read back per step"},
+        "gpu_launches": launches, "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": k["tflops"], "peak": round(peak, 1),
+                     "unit": "TFLOP/s", "frac": round(k["tflops"] / peak, 4), "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" + ("" if fp16 else " / 2 (tf32)"),
+                     "flops_per_launch": klass[dom][2], "ms_per_launch": k["ms_per_launch"]},
+        "kernels": kernels,
+    }
+    if not args.no_eager:
+        try:
+            out["gpu_eager_baseline"] = eager_stem_leg(dev, dev_in, T)
+        except Exception as e:  # noqa: BLE001
+            out["gpu_eager_baseline"] = {"error": repr(e)[:200]}
+    return out
+
+
+def eager_stem_leg(dev, dev_in, T, steps=2):
+    """Stock PyTorch on the same B200: the reference's own ObjDetectCNN (cuDNN) when staged, else the oracle code;
+    fp32, TF32, and half weights + channels_last (the fastest stock configuration).  Baseline tooling only."""
+    import torch
+    from oracle import stem_oracle as S
+    B = dev_in[0].shape[0]
+    out = {"what": "PyTorch eager on the same GPU, 35 per-frame calls per step", "batch": B}
+    if os.path.exists(STEM_REF):
+        ref = _load_reference_stem().to(dev)
+        out["impl"] = "the reference's own ObjDetectCNN"
+    else:
+        P, _ = S.synthetic_stem_case(1, 8, 52, 512, 1)
+        P = {k: v.to(dev) for k, v in P.items()}
+        ref = None
+        out["impl"] = "oracle/stem_oracle.py"
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for tag in ("fp32", "tf32", "fp16_channels_last"):
+            torch.backends.cudnn.allow_tf32 = tag != "fp32"
+            torch.backends.cuda.matmul.allow_tf32 = tag != "fp32"
+            torch.backends.cudnn.benchmark = True
+            if tag == "fp16_channels_last":
+                if ref is None:
+                    continue
+                net = ref.half().to(memory_format=torch.channels_last)
+                xs = [x.half().contiguous(memory_format=torch.channels_last) for x in dev_in]
+                fn = lambda x: net(x)      # noqa: E731
+            else:
+                xs = dev_in
+                fn = (lambda x: ref(x)) if ref is not None else (lambda x: S.stem_forward(P, x))     # noqa: E731
+            with torch.no_grad():
+                for j in range(3):
+                    fn(xs[j % len(xs)])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    for j in range(T):
+                        fn(xs[j % len(xs)])
+                e1.record()
+                torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
             out[tag] = {"ms_per_step": round(ms, 2), "clips_per_s": round(B / ms * 1e3, 2)}
     finally:
@@ -611,6 +841,8 @@ def main():
         if rank != 0:
             return
         iters = max(1, min(args.steps, 3))
+        if args.workload == "stem":
+            args.cpu_clips = 64        # frame images per call of the bounded sample
         cb = cpu_leg(args.workload, args.cpu_clips, iters=iters, warm=min(args.warmup, 1), kind=args.model)
         line = {"impl": "reference",
                 "metric": metric_name(args),
@@ -618,18 +850,28 @@ def main():
                 "warmup": min(args.warmup, 1), "ms_per_step": round(cb["sec_per_step"] * 1e3, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "config": {"workload": workload_name(args),
-                           "sample": f"CPU implementation ({cb['kind']}), each step a bounded sample of "
-                                     f"{args.cpu_clips} clips x 35 frames of that workload"},
+                           "sample": (f"CPU implementation ({cb['kind']}), each step a bounded sample of "
+                                      + (f"{args.cpu_clips} frame images (one call) of that workload"
+                                         if args.workload == "stem" else
+                                         f"{args.cpu_clips} clips x 35 frames of that workload"))},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": round(cb["value"], 4), "unit": "clips/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
-    out = gpu_leg(args)
+    if args.workload == "stem":
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise SystemExit("--workload stem is a single-GPU measurement (the stem shards trivially: replicas only)")
+        out = stem_leg(args)
+    else:
+        out = gpu_leg(args)
     if out is None:
         return
     if args.gpus == 1 and not args.no_cpu:
-        cb = cpu_leg(args.workload, args.cpu_clips, kind=args.model)
+        if args.workload == "stem":
+            cb = cpu_leg("stem", 64, iters=3, warm=1)          # 64 frame images per call, ~10 s of CPU work
+        else:
+            cb = cpu_leg(args.workload, args.cpu_clips, kind=args.model)
         out["cpu_baseline"] = {k: (round(cb[k], 4) if k == "value" else cb[k])
                                for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(out))

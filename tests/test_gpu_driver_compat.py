@@ -10,6 +10,10 @@ feature extractor, puts ``dropin/`` first on PYTHONPATH and executes
     envelope written) + 1 validation iteration, for the attention and the global-pooling model;
   * eval/q_and_v_test.py : restores that checkpoint and runs the test split, whose last batch is short and therefore
     zero-padded with v_len = 1, q_len = 1 clips (eval/q_and_v_test.py:80-87).
+
+The drivers' ``from models.obj_detector import ObjDetectCNN`` (eval/utils.py:4) resolves to the B200 frozen stem too
+(dropin/models/obj_detector.py): it is built by the unmodified ``get_object_detector()``, loads the checkpoint written
+here by the REFERENCE's class and runs once per frame (q_and_v_eval.py:104-110).
 """
 import json
 import os
@@ -128,6 +132,14 @@ def test_unmodified_reference_drivers_run_against_the_dropin(tmp_path, model, ex
     common = ["--model", model, "--batch_size", "4", "--loss_reduction", "sum", "--num_res_blocks", "2",
               "--num_res_block_channels", "64", "--num_input_channels", "512", "--hidden_size", "64", "--embed_size",
               "32", "--checkpoint_path", "ckpt.pt", "--num_workers", "0", *extra]
+    # which classes will the drivers' own import statements get?  (same environment as the driver runs below)
+    probe = os.path.join(tmp, "probe.py")
+    open(probe, "w").write("import sys; sys.path.insert(0, '.')\nfrom models.obj_detector import ObjDetectCNN as O\n"
+                           "from models.film_attn_pt_stem import FiLMAttnPretrainedStem as A\n"
+                           "from models.mac import MACNetwork as M\nprint(O.__module__, A.__module__, M.__module__)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT]), VIDEONAVQA_REFERENCE=REF)
+    mods = subprocess.run([sys.executable, probe], env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert mods == ["videonavqa_b200.models.obj_detector", "videonavqa_b200.models.film_attn_pt_stem", "models.mac"], mods
     out = _run(tmp, "q_and_v_eval.py", *common, "--num_epochs", "1", "--stats_after_every", "1")
     assert "8 train examples, 4 validation examples" in out
     assert "Average loss after 2 iterations in epoch 1" in out           # two training iterations ran

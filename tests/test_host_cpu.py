@@ -152,11 +152,37 @@ def test_dropin_models_package_shim():
         assert a.FiLMAttnPretrainedStem is real.FiLMAttnPretrainedStem
         assert g.FiLMGlobalPoolingPretrainedStem is real.FiLMGlobalPoolingPretrainedStem
         assert t.TimeMultiHopFiLMPretrainedStem is real.TimeMultiHopFiLMPretrainedStem
+        assert importlib.import_module("models.obj_detector").ObjDetectCNN is real.ObjDetectCNN      # frozen stem
     finally:
         sys.path.remove(os.path.join(ROOT, "dropin"))
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_frozen_stem_module_surface(golden_dir):
+    """ObjDetectCNN: constructor of models/obj_detector.py:11-17, state_dict keys / shapes / order of the reference
+    module (recorded in the golden file), weights_init, and no CPU path."""
+    import numpy as np
+    from videonavqa_b200._lib import VnqaError
+    from videonavqa_b200.models import ObjDetectCNN
+    g = np.load(os.path.join(golden_dir, "stem_small.npz"))
+    m = ObjDetectCNN(nb_classes=27, num_filters=int(g["case"][3]), tail_hidden_dim=64, tail_dropout_p=0, logits=True,
+                     pretrained_features=True)
+    assert list(m.state_dict().keys()) == list(g["state_dict_keys"])
+    for k in g.files:
+        if k.startswith("p."):
+            assert tuple(m.state_dict()[k[2:]].shape) == g[k].shape, k
+    assert float(m.conv12.bias.abs().max()) == 0.0 and float(m.fc_tail1.bias.abs().max()) == 0.0   # weights_init
+    big = ObjDetectCNN(nb_classes=27, num_filters=512, tail_hidden_dim=1024, tail_dropout_p=0, logits=True,
+                       pretrained_features=True)                                                   # eval/utils.py:43-48
+    assert big.fc_tail1.weight.shape == (1024, 512 * 30) and big.conv11.weight.shape == (512, 128, 3, 3)
+    with pytest.raises(ValueError, match="multiple of 32"):
+        ObjDetectCNN(27, num_filters=100)
+    with pytest.raises(NotImplementedError):
+        m.train()(torch.zeros(1, 128, 40, 52))
+    with pytest.raises(VnqaError, match="no CPU fallback"):
+        m.eval()(torch.zeros(1, 128, 40, 52))
 
 
 def test_constructor_validates_kernel_constraints():

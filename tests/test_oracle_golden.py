@@ -1,5 +1,7 @@
 """Pin the CPU oracle (oracle/film_oracle.py) against the golden vectors produced by the
 unmodified reference modules (oracle/gen_golden.py).  CPU only."""
+import os
+
 import pytest
 import torch
 
@@ -96,3 +98,25 @@ def test_operand_rounding_emulation_stays_near_the_reference(name):
     lo, _, _, _ = O.loss_and_grads(kind, params, O.new_bn_state(C), O.new_film_state(kw["batch_size"], kw["hidden_size"]),
                                    b["v"], b["q"], b["v_lens"], b["q_lens"], b["labels"], training=True)
     assert norm_max_err(lo, torch.from_numpy(z["logits_train"])) <= 2e-5
+
+
+def test_stem_oracle_matches_the_reference_module(golden_dir):
+    """oracle/stem_oracle.py against the output of the UNMODIFIED reference ObjDetectCNN (oracle/gen_golden_stem.py),
+    fp32 and fp64; the operand-rounding emulation stays within the bound the GPU tests use."""
+    import hashlib
+    import numpy as np
+    from oracle import stem_oracle as S
+    g = np.load(os.path.join(golden_dir, "stem_small.npz"))
+    P, x = S.synthetic_stem_case(*[int(v) for v in g["case"]])
+    assert hashlib.sha256(x.numpy().tobytes()).digest() == g["x_sha256"].tobytes(), "numpy RNG drift"
+    for k, v in P.items():
+        assert np.array_equal(v.numpy(), g["p." + k]), k
+    y = S.stem_forward(P, x)
+    scale = float(np.abs(g["y"]).max())
+    assert float((y - torch.from_numpy(g["y"])).abs().max()) <= 5e-5 * scale          # fp32: summation order only
+    y64 = S.stem_forward(P, x, dtype=torch.float64)
+    assert float((y64 - torch.from_numpy(g["y64"])).abs().max()) <= 1e-10 * scale
+    for emulate in ("fp16", "tf32"):
+        ye = S.stem_forward(P, x, emulate=emulate).double()
+        rel = float((ye - y64).norm() / y64.norm())
+        assert 1e-5 < rel <= 1.5e-3, (emulate, rel)

@@ -16,11 +16,29 @@ from videonavqa_b200 import ops  # noqa: E402
 from videonavqa_b200._lib import EPI_BIAS_RELU, EPI_DGRAD_RES, EPI_FILM, EPI_PLAIN  # noqa: E402
 
 
+def stem(a):
+    """ncu -k regex:'conv_gemm_kernel|nchw_to_nhwc|nhwc_to_nchw' ... python tools/ncu_targets.py --stem"""
+    from videonavqa_b200.models import ObjDetectCNN
+    torch.manual_seed(0)
+    m = ObjDetectCNN(27, num_filters=512, tail_hidden_dim=1024, tail_dropout_p=0, logits=True,
+                     pretrained_features=True).cuda().eval().set_operands(a.operands)
+    x = torch.randn(64, 128, 40, 52, device="cuda").clamp_min_(0)
+    m(x)                                       # packs the weights (not a target)
+    torch.cuda.synchronize()
+    for _ in range(a.reps):
+        m(x)
+        torch.cuda.synchronize()
+    print("ncu stem target done", a.operands)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--operands", choices=["fp16", "tf32"], default="fp16")
     ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--stem", action="store_true", help="one call of the frozen stem (64 frames) instead of the trunk kernels")
     a = ap.parse_args()
+    if a.stem:
+        return stem(a)
     act = 1 if a.operands == "fp16" else 0
     dt = ops.act_dtype(act)
     dev = torch.device("cuda")
