@@ -49,6 +49,12 @@ int vnqa_debug_build(void);
  * img_of[b*T + t] is the image index of (clip b, frame t), or -1 when t >= v_lens[b]. */
 int vnqa_frames_to_nhwc(const float* v_input, void* x_out, const int32_t* img_of, int32_t B, int32_t C, int32_t T,
                         int32_t act_dtype, void* stream);
+/* Same result from FRAME-BLOCKED memory: frame t of clip b is one contiguous (C, 10, 13) block at
+ * v_input + b*stride_b + t*stride_t (strides in floats).  This is the (B, C, 10, 13, T) VIEW the reference's drivers
+ * build from the per-frame stem outputs (torch.stack(...).permute(1, 2, 3, 4, 0)[perm_idx], q_and_v_eval.py:110-116);
+ * reading it in place saves a 2 x 596 MB relayout pass. */
+int vnqa_frames_blocked_to_nhwc(const float* v_input, void* x_out, const int32_t* img_of, int32_t B, int32_t C, int32_t T,
+                                int64_t stride_b, int64_t stride_t, int32_t act_dtype, void* stream);
 /* (no backward: v_input needs no gradient - the stem is frozen, eval/q_and_v_eval.py:101-110) */
 
 /* ---- weight packing (derived caches; PyTorch-native layouts stay the source of truth).

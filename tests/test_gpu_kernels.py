@@ -47,6 +47,34 @@ def test_frames_to_nhwc_is_exact_tf32_rounding():
         assert torch.equal(xh[int(img_of[b, t])], ref)
 
 
+@pytest.mark.parametrize("C", [64, 96, 512])
+def test_frames_to_nhwc_reads_the_drivers_frame_blocked_view_in_place(C):
+    """The reference's drivers hand the model torch.stack(per-frame maps).permute(1, 2, 3, 4, 0)[perm_idx]
+    (eval/q_and_v_eval.py:110-116): a (B, C, 10, 13, T)-shaped view of (B, T, C, 10, 13)-ordered memory.  K0 reads it in
+    place (frames_blocked_to_nhwc_kernel) with the same bits as the T-innermost kernel on the contiguous copy."""
+    from videonavqa_b200 import ops
+    from videonavqa_b200.engine import Plan
+    B, T = 6, 35
+    g = torch.Generator(device="cuda").manual_seed(C)
+    frames = [torch.randn(B, C, 10, 13, device="cuda", generator=g).clamp_min_(0) for _ in range(T)]
+    view = torch.stack(frames).permute(1, 2, 3, 4, 0)                       # q_and_v_eval.py:110
+    perm = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    view = view[perm]                                                       # :114-116
+    assert not view.is_contiguous() and view.stride()[1:4] == (130, 13, 1)
+    plan = Plan([35, 33, 20, 20, 7, 1], B, T, torch.device("cuda"))
+    for act in (0, 1):
+        got = ops.frames_to_nhwc(view, plan.img_of, plan.n_img, act)
+        want = ops.frames_to_nhwc(view.contiguous(), plan.img_of, plan.n_img, act)
+        assert torch.equal(got, want)
+    # a plain permuted stack (no index) and a view with any other stride pattern (falls back to .contiguous())
+    v2 = torch.stack(frames).permute(1, 2, 3, 4, 0)
+    assert torch.equal(ops.frames_to_nhwc(v2, plan.img_of, plan.n_img, 1),
+                       ops.frames_to_nhwc(v2.contiguous(), plan.img_of, plan.n_img, 1))
+    v3 = view.contiguous().transpose(2, 3).contiguous().transpose(2, 3)
+    assert torch.equal(ops.frames_to_nhwc(v3, plan.img_of, plan.n_img, 1),
+                       ops.frames_to_nhwc(v3.contiguous(), plan.img_of, plan.n_img, 1))
+
+
 def test_sgemm_variants_match_fp64():
     from videonavqa_b200 import ops
     g = torch.Generator().manual_seed(0)

@@ -80,6 +80,57 @@ static int launch_k0(const float* v_input, void* x_out, const int32_t* img_of, i
   return 0;
 }
 
+// K0 for FRAME-BLOCKED input: every (clip, frame) is one contiguous (C, 130) NCHW block at v + b*stride_b + t*stride_t.
+// That is what the reference's drivers hand to the model: torch.stack(per-frame stem outputs).permute(1,2,3,4,0)
+// followed by the length sort v_inputs[perm_idx] (eval/q_and_v_eval.py:110-116) is a (B, C, 10, 13, T)-shaped VIEW of
+// memory ordered (B, T, C, 10, 13).  Reading it directly saves the .contiguous() pass (596 MB read + written) that the
+// T-innermost kernel above would need.  One block per (channel slab, frame image): CH*130 contiguous floats in, 130
+// rows of 128 bytes out.
+template <typename T, int CH>
+__global__ void __launch_bounds__(256) frames_blocked_to_nhwc_kernel(const float* __restrict__ v, T* __restrict__ x,
+                                                                     const int* __restrict__ img_of, int C, int Tn,
+                                                                     long long stride_b, long long stride_t) {
+  constexpr int PITCH = VNQA_IMG_PIX + 1;
+  __shared__ float tile[CH * PITCH];
+  const int cs = blockIdx.x, bt = blockIdx.y;
+  const int img = __ldg(img_of + bt);
+  if (img < 0) return;
+  const int b = bt / Tn, t = bt - b * Tn;
+  const int nc = min(CH, C - cs * CH);
+  const float* src = v + b * stride_b + t * stride_t + (long long)cs * CH * VNQA_IMG_PIX;
+  const int total = nc * VNQA_IMG_PIX;
+  constexpr int U = 4;
+  for (int i0 = threadIdx.x; i0 < total; i0 += U * 256) {
+    float val[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) val[u] = (i0 + u * 256 < total) ? __ldg(src + i0 + u * 256) : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 256;
+      if (i < total) {
+        const int c = i / VNQA_IMG_PIX;
+        tile[c * PITCH + (i - c * VNQA_IMG_PIX)] = val[u];
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  constexpr int PER_LANE = CH / 32;
+  if (PER_LANE * lane >= nc) return;
+  T* dst0 = x + (long long)img * VNQA_IMG_PIX * C + cs * CH + PER_LANE * lane;
+  for (int p = threadIdx.x >> 5; p < VNQA_IMG_PIX; p += 8) {
+    T* dst = dst0 + (long long)p * C;
+    if (PER_LANE == 1) {
+      Op<T>::st(dst, tile[lane * PITCH + p], 0);
+    } else {
+      T pair[2];
+      Op<T>::st(&pair[0], tile[(2 * lane) * PITCH + p], 0);
+      Op<T>::st(&pair[1], tile[(2 * lane + 1) * PITCH + p], 0);
+      *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(pair);
+    }
+  }
+}
+
 // (Cout, Cin, taps) -> [tap][rows_pad][Cin]   (forward operand), or
 // (Cout, Cin, taps) -> [taps-1-tap][rows_pad >= Cin][Cout]   (data-gradient operand: mirrored taps, in/out swapped)
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin,
@@ -132,6 +183,25 @@ extern "C" int vnqa_frames_to_nhwc(const float* v_input, void* x_out, const int3
   VNQA_REQUIRE(T > 0 && T <= 64 && B > 0 && B <= 65535, "vnqa_frames_to_nhwc: bad B/T (%d, %d)", B, T);
   return act_dtype == VNQA_ACT_FP16 ? launch_k0<__half, 64>(v_input, x_out, img_of, B, C, T, as_stream(stream))
                                     : launch_k0<float, 32>(v_input, x_out, img_of, B, C, T, as_stream(stream));
+}
+
+extern "C" int vnqa_frames_blocked_to_nhwc(const float* v_input, void* x_out, const int32_t* img_of, int32_t B, int32_t C,
+                                           int32_t T, int64_t stride_b, int64_t stride_t, int32_t act_dtype,
+                                           void* stream) {
+  VNQA_REQUIRE(v_input && x_out && img_of, "vnqa_frames_blocked_to_nhwc: null pointer");
+  VNQA_REQUIRE(C % 32 == 0 && C > 0, "vnqa_frames_blocked_to_nhwc: C must be a multiple of 32 (got %d)", C);
+  VNQA_REQUIRE(T > 0 && B > 0 && (long long)B * T <= 65535, "vnqa_frames_blocked_to_nhwc: bad B/T (%d, %d)", B, T);
+  if (act_dtype == VNQA_ACT_FP16) {
+    dim3 grid((C + 63) / 64, B * T);
+    frames_blocked_to_nhwc_kernel<__half, 64><<<grid, 256, 0, as_stream(stream)>>>(
+        v_input, static_cast<__half*>(x_out), img_of, C, T, stride_b, stride_t);
+  } else {
+    dim3 grid((C + 31) / 32, B * T);
+    frames_blocked_to_nhwc_kernel<float, 32><<<grid, 256, 0, as_stream(stream)>>>(
+        v_input, static_cast<float*>(x_out), img_of, C, T, stride_b, stride_t);
+  }
+  VNQA_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int vnqa_pack_conv_weight(const float* w, void* packed_, int32_t cout, int32_t cin, int32_t taps,

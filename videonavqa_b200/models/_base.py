@@ -135,7 +135,7 @@ class FilmModuleBase(nn.Module):
         names, tensors = self._collect_params()
         self._param_names = names
         need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
-        return _FilmFunction.apply(self, need_grad, v_input.float().contiguous(), q_input, v_lens, q_lens, *tensors)
+        return _FilmFunction.apply(self, need_grad, v_input.float(), q_input, v_lens, q_lens, *tensors)
 
     def _host_lens(self, v_lens, q_lens, dev):
         """Clip / question lengths on the host.  The reference reads them from the device >= 70 times per forward

@@ -82,11 +82,22 @@ def act_dtype(act):
 
 
 def frames_to_nhwc(v_input, img_of, n_img, act=0):
+    """(B, C, 10, 13, T) fp32 -> frame-image-major NHWC [n_img][130][C].  Two memory layouts are read in place: the
+    contiguous one (T innermost) and the frame-blocked view the reference's drivers build from per-frame stem outputs
+    (every (b, t) a contiguous (C, 10, 13) block); anything else is made contiguous first."""
     B, C, H, W, T = v_input.shape
-    assert (H, W) == (10, 13)
+    assert (H, W) == (10, 13) and v_input.dtype == torch.float32
     x = torch.empty(n_img, IMG_PIX, C, device=v_input.device, dtype=act_dtype(act))
-    check(_lib.lib().vnqa_frames_to_nhwc(_p(_f32c(v_input)), _p(x), _p(img_of), B, C, T, act, _stream()),
-          "frames_to_nhwc")
+    sb, sc, sh, sw, st = v_input.stride()
+    if not v_input.is_contiguous() and (sc, sh, sw) == (IMG_PIX, W, 1) and (B == 1 or sb >= C * IMG_PIX) \
+            and (T == 1 or st >= C * IMG_PIX):
+        with _timed("hbm.k0_blocked", float(n_img * IMG_PIX * C * (4 + x.element_size()))):
+            check(_lib.lib().vnqa_frames_blocked_to_nhwc(_p(v_input), _p(x), _p(img_of), B, C, T, sb, st, act,
+                                                         _stream()), "frames_blocked_to_nhwc")
+        return x
+    v_input = v_input.contiguous()
+    with _timed("hbm.k0", float(n_img * IMG_PIX * C * (4 + x.element_size()))):
+        check(_lib.lib().vnqa_frames_to_nhwc(_p(v_input), _p(x), _p(img_of), B, C, T, act, _stream()), "frames_to_nhwc")
     return x
 
 
