@@ -50,8 +50,9 @@ struct Cfg {
   static constexpr int B_BYTES = B_ROWS * ROW_BYTES;       // 26624 / 13312 (multiples of 1024)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 43008 / 29696
   static constexpr int STAGES = NCTA == 1 ? 5 : 7;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, scheduler ring*/;
 };
+constexpr int CLC_D = 4;           // depth of the scheduler's response ring (one request is in flight at a time)
 
 struct KParams {
   int taps, k_chunks, m_tiles, n_tiles, splits, rows_pad, flat, cout, n_img, no_round;
@@ -59,6 +60,7 @@ struct KParams {
   // image geometry (conv): W = 13 << g_shift, H = 2 * rp; a tile is (8 >> g_shift) images x 2 rows x W = 208 pixels,
   // i.e. 8 groups of 26 consecutive output rows, (1 << g_shift) groups per image
   int rp, g_shift, hw, w2, pool;
+  int dynamic;                 // 1: tiles are handed out by cluster launch control (grid = one cluster per work item)
   long long out_split_stride;  // PARTIAL: n_img * cout
   void* out;
   const float* bias;
@@ -93,6 +95,56 @@ __device__ __forceinline__ TileCoord decode_tile(int item, const KParams& p, int
   t.sp = r / p.n_tiles;
   return t;
 }
+
+// Tile scheduler.  Every role warp (TMA producer, MMA issuer, epilogue) of every CTA of the cluster walks the same
+// sequence of work items.  Static mode: item = cluster id + k * number of clusters (persistent grid).  Dynamic mode
+// (cluster launch control): the grid has ONE cluster per work item, the hardware starts as many as fit, and a running
+// cluster, instead of exiting after its own item, asks to cancel a not-yet-launched cluster and takes over its item:
+// clusters that start late (SMs still busy with the side stream or with NCCL) or run slowly simply take fewer items.
+// The leader CTA's producer warp issues ONE request when it starts an item (the response - multicast to both CTAs -
+// names the item after it); every role warp consumes each response once and then arrives on the leader's `empty`
+// barrier of that ring slot.
+template <int NCTA>
+struct TileSched {
+  static constexpr int CONSUMERS = NCTA == 2 ? 11 : 6;   // leader: producer, MMA, 4 epilogue warps; peer: producer, 4 epilogue
+  uint64_t* full;
+  uint64_t* empty;
+  uint4* resp;
+  int dynamic, total, stride;
+  int q;        // responses consumed (consumers) / requests issued (the leader's producer keeps a second counter)
+  int qi;
+
+  __device__ __forceinline__ int first() const { return (int)blockIdx.x / NCTA; }
+
+  __device__ __forceinline__ void request(int lane) {     // leader producer warp only, warp-uniform
+    if (!dynamic) return;
+    const int s = qi % CLC_D;
+    mbar_wait(&empty[s], (((qi / CLC_D) & 1) ^ 1));
+    if (NCTA == 2) { if (lane < 2) mbar_expect_tx_remote(&full[s], 16, lane); }
+    else if (lane == 0) mbar_expect_tx(&full[s], 16);
+    __syncwarp();
+    if (lane == 0) clc_try_cancel<NCTA == 2>(&resp[s], &full[s]);
+    ++qi;
+  }
+
+  __device__ __forceinline__ int next(int item, int lane, bool leader) {   // warp-uniform
+    if (!dynamic) {
+      const int n = item + stride;
+      return n < total ? n : -1;
+    }
+    const int s = q % CLC_D;
+    mbar_wait(&full[s], (q / CLC_D) & 1);
+    const int x = clc_response_ctaid_x(&resp[s]);
+    fence_proxy_async();      // this read of the response is ordered before the async-proxy write of a later response
+    __syncwarp();
+    if (lane == 0) {
+      if (leader) mbar_arrive(&empty[s]);
+      else mbar_arrive_remote(&empty[s], 0);
+    }
+    ++q;
+    return x < 0 ? -1 : x / NCTA;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------ epilogue
 // One accumulator tile (128 channels x 208 pixels) from TMEM to global memory; thread = output channel.
@@ -291,16 +343,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* acc_full = empty_bar + C::STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* clc_full = acc_empty + 2;
+  uint64_t* clc_empty = clc_full + CLC_D;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(clc_empty + CLC_D);
+  uint4* clc_resp = reinterpret_cast<uint4*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;
   const bool leader = rank == 0;
-  const int total_items = (p.m_tiles / NCTA) * p.n_tiles * p.splits;
-  const int first_item = blockIdx.x / NCTA;
-  const int item_stride = gridDim.x / NCTA;
   const int k_iters = p.taps * p.k_chunks;
+  TileSched<NCTA> sched{clc_full, clc_empty, clc_resp, p.dynamic, (p.m_tiles / NCTA) * p.n_tiles * p.splits,
+                        (int)gridDim.x / NCTA, 0, 0};
   const DbgCtx dbg{p.dbg, full_bar, 2 * C::STAGES + 4};
   (void)dbg;
 
@@ -314,6 +368,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4 * NCTA);   // one arrive per epilogue warp of every CTA
+    }
+    for (int i = 0; i < CLC_D; ++i) {
+      mbar_init(&clc_full[i], 1);           // the expect_tx arrival (+ 16 response bytes)
+      mbar_init(&clc_empty[i], TileSched<NCTA>::CONSUMERS);
     }
     fence_mbar_init();
   }
@@ -338,7 +396,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (every CTA)
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = first_item; item < total_items; item += item_stride) {
+    for (int item = sched.first(); item >= 0; item = sched.next(item, lane, leader)) {
+      if (leader) sched.request(lane);      // ask now for the item after this one
       const TileCoord tc = decode_tile<NCTA>(item, p, rank);
       const int a_row0 = tc.mt * BM;
       int b1, b2, b3;  // B box coordinates of dims 1..3 before the tap shift
@@ -382,7 +441,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int item = first_item; item < total_items; item += item_stride) {
+    for (int item = sched.first(); item >= 0; item = sched.next(item, lane, true)) {
       MBAR_WAIT(&acc_empty[as], aphase ^ 1, 2, ((long long)item << 20));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * ACC_COLS;
@@ -417,7 +476,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
     int as = 0;
     uint32_t aphase = 0;
-    for (int item = first_item; item < total_items; item += item_stride) {
+    for (int item = sched.first(); item >= 0; item = sched.next(item, lane, leader)) {
       const TileCoord tc = decode_tile<NCTA>(item, p, rank);
       MBAR_WAIT(&acc_full[as], aphase, 4, ((long long)item << 20));
       tc_fence_after();
@@ -460,7 +519,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams&
   }
   const int items = (kp.m_tiles / NCTA) * kp.n_tiles * kp.splits;
   const int groups = sms / NCTA;
-  const int grid = (items < groups ? items : groups) * NCTA;
+  // dynamic: one cluster per work item, handed out by cluster launch control; static: persistent grid, round robin
+  const int grid = (kp.dynamic || items < groups ? items : groups) * NCTA;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -481,6 +541,12 @@ template <int EPI, typename T>
 static int launch_any(int ncta, const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, int sms,
                       cudaStream_t st) {
   return ncta == 2 ? launch<EPI, 2, T>(tmA, tmB, kp, sms, st) : launch<EPI, 1, T>(tmA, tmB, kp, sms, st);
+}
+
+// A/B switch VNQA_TILE_SCHED=static (persistent grid with the round-robin schedule of round 1), read once
+static int dynamic_sched() {
+  static const int v = [] { const char* e = getenv("VNQA_TILE_SCHED"); return (e && e[0] == 's') ? 0 : 1; }();
+  return v;
 }
 
 // bring-up switch VNQA_CONV_NCTA=1 (single-CTA kernels everywhere), read once
@@ -540,6 +606,7 @@ static int conv_gemm_typed(const vnqa_conv_args* a, cudaStream_t st) {
   kp.res = a->res; kp.z_out = a->z_out; kp.add = a->add; kp.dbias = a->dbias;
   kp.grad_unscale = a->grad_unscale == 0.f ? 1.f : a->grad_unscale;
   kp.dbg = debug_buffer();
+  kp.dynamic = dynamic_sched();
 
   // CTA pairs (cta_group::2) whenever the output channels split into an even number of 128-row tiles
   int ncta = (kp.m_tiles % 2 == 0) ? 2 : 1;

@@ -295,6 +295,50 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+// arrive + expect `bytes` on the mbarrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_expect_tx_remote(uint64_t* bar, uint32_t bytes, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %2;\n"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(cta)
+      : "memory");
+}
+
+// ---- cluster launch control (dynamic tile scheduling in hardware): a running cluster asks to CANCEL a cluster of the
+// same grid that has not been launched yet and, when that succeeds, does its work instead.  The 16-byte response lands
+// in shared memory (in every CTA of the cluster with MULTICAST) and completes 16 bytes on the mbarrier.
+template <bool MULTICAST>
+__device__ __forceinline__ void clc_try_cancel(void* resp16, uint64_t* bar) {
+  if (MULTICAST)
+    asm volatile(
+        "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+        "[%0], [%1];" ::"r"(smem_u32(resp16)), "r"(smem_u32(bar)) : "memory");
+  else
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                     smem_u32(resp16)), "r"(smem_u32(bar)) : "memory");
+}
+// first CTA id (x) of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_response_ctaid_x(const void* resp16) {
+  uint32_t valid, x;
+  asm volatile(
+      "{\n"
+      ".reg .pred p1;\n"
+      ".reg .b128 r;\n"
+      "ld.shared.b128 r, [%2];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n"
+      "selp.u32 %0, 1, 0, p1;\n"
+      "mov.u32 %1, 0;\n"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, r;\n"
+      "}\n"
+      : "=r"(valid), "=r"(x)
+      : "r"(smem_u32(resp16))
+      : "memory");
+  return valid ? (int)x : -1;
+}
+
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* leader_bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
