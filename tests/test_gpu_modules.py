@@ -150,6 +150,46 @@ def test_state_carried_without_init_hidden():
     assert not torch.equal(a1, a2)
 
 
+@pytest.mark.parametrize("operands", ["tf32", "fp16"])
+def test_carried_state_with_tied_question_lengths(operands):
+    """Q3 with TIED q_lens: the question-LSTM state is kept in q_len-sorted order between calls
+    (film_attn_pt_stem.py:153-160); with ties the sort must put every clip back on its own state on the next call.
+    Two forwards without init_hidden() against the oracle, which indexes the state by clip and never sorts.  The
+    golden weights forget their initial state within a frame or two, so the forget-gate bias is raised to 4 (long
+    memory) and the clips are 2-3 frames long: swapping the states of the two tied clips then moves the second call's
+    logits by 2.6e-2 (oracle, below), 26 x the tolerance."""
+    kind, kw, params, _, b, _ = load_case("attn_small")
+    H = kw["hidden_size"]
+    params = dict(params)
+    bh = params["film_layer.0.bias_hh_l0"].clone()
+    bh[H:2 * H] = 4.0
+    params["film_layer.0.bias_hh_l0"] = bh
+    m = build_module(kind, kw, params, operands).eval()
+    q_lens = torch.tensor([5, 9, 9])                       # clips 1 and 2 tied, clip 0 sorts last
+    v_lens = torch.tensor([3, 3, 2])
+    q = b["q"].clone().clamp_min(1)
+    q[torch.arange(q.shape[1])[None, :] >= q_lens[:, None]] = 0
+    with torch.no_grad():
+        m.init_hidden()
+        a1 = m(b["v"].cuda(), q.cuda(), v_lens.cuda(), q_lens.cuda())
+        a2 = m(b["v"].cuda(), q.cuda(), v_lens.cuda(), q_lens.cuda())     # carried state
+    bn = O.new_bn_state(kw["num_res_block_channels"])
+    st = O.new_film_state(kw["batch_size"], H)
+    with torch.no_grad():
+        r1, st1 = O.film_attn_forward(params, bn, st, b["v"], q, v_lens, q_lens, training=False)
+        r2, st2 = O.film_attn_forward(params, bn, st1, b["v"], q, v_lens, q_lens, training=False)
+        swapped = (st1[0][[0, 2, 1]], st1[1][[0, 2, 1]])
+        r2s, _ = O.film_attn_forward(params, bn, swapped, b["v"], q, v_lens, q_lens, training=False)
+    assert norm_max_err(r2s, r2) > 1e-2 and norm_max_err(r1, r2) > 1e-2      # the test can tell
+    assert norm_max_err(a1.cpu(), r1) <= 1e-3
+    assert norm_max_err(a2.cpu(), r2) <= 1e-3
+    # the carried state itself: the module's rows (kept in its sorted order) are the oracle's per-clip rows
+    for mine, want in ((m.film_hidden[0][0].cpu(), st2[0]), (m.film_hidden[1][0].cpu(), st2[1])):
+        d = torch.cdist(want.double(), mine.double())
+        assert sorted(d.argmin(dim=1).tolist()) == [0, 1, 2]
+        assert float(d.min(dim=1).values.max()) <= 2e-3 * float(want.norm(dim=1).min())
+
+
 def test_batch_size_and_frame_lock():
     """Quirk Q7."""
     kind, kw, params, _, b, _ = load_case("attn_small")
