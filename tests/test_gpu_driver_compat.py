@@ -7,7 +7,7 @@ labels / split / q_ids json, a random-init ObjDetectCNN checkpoint), a ``demo`` 
 feature extractor, puts ``dropin/`` first on PYTHONPATH and executes
 
   * eval/q_and_v_eval.py : 2 training iterations (forward, CrossEntropy(sum), backward, clip_grad_norm, Adam, checkpoint
-    envelope written) + 1 validation iteration, for the attention and the global-pooling model;
+    envelope written) + 1 validation iteration, for the attention, global-pooling and multi-hop models;
   * eval/q_and_v_test.py : restores that checkpoint and runs the test split, whose last batch is short and therefore
     zero-padded with v_len = 1, q_len = 1 clips (eval/q_and_v_test.py:80-87).
 
@@ -124,6 +124,7 @@ def _run(tmp, script, *argv):
 @pytest.mark.parametrize("model,extra", [
     ("film_attn_pt", ["--at_hidden_size", "64"]),
     ("film_gp_pt", ["--num_tail_channels", "16"]),
+    ("time_multi_hop", ["--num_tail_channels", "16"]),
 ])
 def test_unmodified_reference_drivers_run_against_the_dropin(tmp_path, model, extra):
     assert os.path.isdir(REF), "oracle/_ref/reference is missing: run __graft_entry__.build() (oracle/stage_ref.py)"
@@ -149,7 +150,10 @@ def test_unmodified_reference_drivers_run_against_the_dropin(tmp_path, model, ex
     saved = torch.load(ck, map_location="cpu", weights_only=False)
     assert set(saved) == {"epoch", "model", "state_dict", "train_f1w", "train_f1micro", "optimizer"}
     assert not any(k.startswith("conv1x1_layers") for k in saved["state_dict"])           # quirk Q1
-    assert "film_layer.0.weight_ih_l0" in saved["state_dict"]                              # quirk Q2 (CUDA branch)
+    if model != "time_multi_hop":
+        assert "film_layer.0.weight_ih_l0" in saved["state_dict"]                          # quirk Q2 (CUDA branch)
+    else:
+        assert "q_encoder.weight_ih_l0" in saved["state_dict"] and "decoder_norm.weight" in saved["state_dict"]
     assert all(np.isfinite(v.float().numpy()).all() for v in saved["state_dict"].values())
     # the test driver restores that checkpoint; 6 test clips at batch 4 -> the second batch is padded with 2 dummies
     os.replace(ck, os.path.join(tmp, "eval", "ckpt.pt"))
