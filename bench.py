@@ -60,6 +60,12 @@ def parse():
     ap.add_argument("--optimizer", choices=["fused", "torch"], default="fused",
                     help="fused = videonavqa_b200.optim.FusedClipAdam over the flat bucket; torch = clip_grad_norm_ + Adam")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager baseline on the same GPU")
+    ap.add_argument("--run-ahead", type=int, default=int(os.environ.get("BENCH_RUN_AHEAD", "0")),
+                    help="device-resident loop: the host may be at most this many steps ahead of the GPU (it waits on the "
+                         "event of step i - K before enqueuing step i + 1; 0 = unbounded).  The GPU queue never drains.")
+    ap.add_argument("--graph", action="store_true",
+                    help="also capture the train step in a CUDA graph (videonavqa_b200.graph) and time its replays; "
+                         "single GPU, attn / gp, fused optimizer")
     ap.add_argument("--operands", choices=["fp16", "tf32"], default=None,
                     help="operand storage of the tensor-core kernels (default: the package default / VNQA_OPERANDS)")
     return ap.parse_args()
@@ -601,7 +607,7 @@ def gpu_leg(args):
         # eval.sh:16 (Adam, lr 1e-4) + q_and_v_eval.py:137 (clip_grad_norm 1.0): fused over flat buffers by default,
         # --optimizer torch = the reference's own two calls (A/B)
         if fused:
-            opt = FusedClipAdam(model.parameters(), lr=1e-4, max_norm=1.0).attach(model)
+            opt = FusedClipAdam(model.parameters(), lr=1e-4, max_norm=1.0, capturable=args.graph).attach(model)
         else:
             opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     _log("model on device")
@@ -664,8 +670,15 @@ def gpu_leg(args):
     opt_launches[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    done = []
+    for i in range(args.steps):
         step(*dev_in)
+        if args.run_ahead > 0:
+            # bounded run-ahead, as a training loop that logs its loss every few iterations has anyway: the GPU always
+            # has >= 1 step queued, the host never piles up a deep launch queue
+            ev = torch.cuda.Event(); ev.record(); done.append(ev)
+            if i >= args.run_ahead:
+                done[i - args.run_ahead].synchronize()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
@@ -737,6 +750,34 @@ def gpu_leg(args):
     e2e_ms = f0.elapsed_time(f1) / args.steps
     _log(f"e2e timing done: {e2e_ms:.2f} ms/step")
 
+    graph_info = None
+    if args.graph and world == 1 and fused and args.model != "tmh":
+        from videonavqa_b200.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt, dev_in[0], dev_in[1], host[2], dev_in[3], dev_in[4],
+                                 loss_fn=torch.nn.CrossEntropyLoss(reduction="sum"))
+        for _ in range(2):
+            gstep()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        g0.record()
+        for _ in range(args.steps):
+            gstep()
+        g1.record()
+        host_s = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        # host time of the eager loop for comparison: enqueue only, no synchronisation inside
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step(*dev_in)
+        eager_host_s = (time.perf_counter() - t0) / 3
+        torch.cuda.synchronize()
+        graph_info = {"ms_per_step": round(g0.elapsed_time(g1) / args.steps, 3),
+                      "host_ms_per_replay": round(host_s / args.steps * 1e3, 3),
+                      "host_ms_per_eager_step_enqueue": round(eager_host_s * 1e3, 3),
+                      "what": "GraphedTrainStep: init_hidden + fwd + CE(sum) + bwd + fused clip/Adam as one graph"}
+        _log(f"graph replay: {graph_info}")
+
     dp_check = None
     if world > 1:
         tt = torch.tensor([ms, e2e_ms], dtype=torch.float64)
@@ -805,7 +846,8 @@ def gpu_leg(args):
                    "step": ("fwd+CE(sum)+bwd" + ("+allreduce(sum, overlapped)" if world > 1 else "") +
                             ("+fused clip_grad_norm/Adam" if fused else "+clip_grad_norm+Adam")) if train
                    else "eval forward", "l2": "inputs larger than L2 (v_input 596 MB, activations 1.19 GB each)",
-                   "frame_images_per_step": n_frames_total * world},
+                   "frame_images_per_step": n_frames_total * world,
+                   "host_run_ahead_steps": args.run_ahead or "unbounded"},
         "model_tflops": round(clips * gflop * scale / ms, 1),
         "e2e": {"value": round(clips / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 3),
@@ -816,6 +858,8 @@ def gpu_leg(args):
         "roofline_hbm": hbm_roofline(kernels, peaks, load_traffic(model.precision.name)),
         "kernels": kernels,
     }
+    if graph_info is not None:
+        out["cuda_graph"] = graph_info
     if reducer is not None:
         out["allreduce_bytes_per_step"] = reducer.last_bytes
         out["dp_check"] = dp_check

@@ -261,6 +261,11 @@ int vnqa_sumsq_partials(const float* g, int64_t n, double* partials, void* strea
 int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const double* partials, int32_t n_partials,
                    float grad_scale, float max_norm, double lr, double beta1, double beta2, double eps, int64_t step,
                    float* norm_out, void* stream);
+/* Same update with the step count kept ON THE DEVICE (*step_dev is incremented, then used): nothing in the launch
+ * depends on a host-side counter, so a captured CUDA graph of the train step can be replayed. */
+int vnqa_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const double* partials,
+                       int32_t n_partials, float grad_scale, float max_norm, double lr, double beta1, double beta2,
+                       double eps, int64_t* step_dev, float* norm_out, void* stream);
 
 /* ---- K10 (new - the reference is single-GPU): gradient all-reduce over NVLink / NVSwitch.
  * One process per GPU owns one ncclComm_t and one dedicated communication stream inside the library.  NCCL is

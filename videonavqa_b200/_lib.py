@@ -95,6 +95,7 @@ SIGNATURES = {
     "vnqa_opt_num_partials": [],
     "vnqa_sumsq_partials": [P, I64, P, P],
     "vnqa_clip_adam": [P, P, P, P, I64, P, I32, F32, F32, c_double, c_double, c_double, c_double, I64, P, P],
+    "vnqa_clip_adam_dev": [P, P, P, P, I64, P, I32, F32, F32, c_double, c_double, c_double, c_double, P, P, P],
     "vnqa_attn_tail_forward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
     "vnqa_attn_tail_backward": [P, P, I32, I32, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P],
 }

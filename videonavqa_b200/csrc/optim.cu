@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adam_kernel(float4* __restri
                                                                 int n_partials, float grad_scale, float max_norm,
                                                                 float step_size, float beta2, float w1, float w2,
                                                                 float eps, float bias_correction2_sqrt,
-                                                                float* __restrict__ norm_out) {
+                                                                float* __restrict__ norm_out,
+                                                                const long long* __restrict__ step_dev, double lr,
+                                                                double beta1_d, double beta2_d) {
   // every block sums the same partials in the same order -> identical coef everywhere, run to run
   __shared__ double red[OPT_THREADS];
   double s = 0.0;
@@ -57,6 +59,19 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adam_kernel(float4* __restri
   for (int o = OPT_THREADS / 2; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
+  }
+  if (step_dev != nullptr) {
+    // capturable mode (CUDA graphs): the step count lives on the device, so the bias corrections are formed here -
+    // in double, exactly like the host path - by one thread per block
+    __shared__ float sc[2];
+    if (threadIdx.x == 0) {
+      const double t = (double)*step_dev;
+      sc[0] = (float)(lr / (1.0 - pow(beta1_d, t)));
+      sc[1] = (float)sqrt(1.0 - pow(beta2_d, t));
+    }
+    __syncthreads();
+    step_size = sc[0];
+    bias_correction2_sqrt = sc[1];
   }
   float coef = grad_scale;
   if (max_norm > 0.f) {
@@ -82,6 +97,8 @@ __global__ void __launch_bounds__(OPT_THREADS) clip_adam_kernel(float4* __restri
   }
 }
 
+__global__ void adam_step_inc_kernel(long long* step_dev) { *step_dev += 1; }
+
 }  // namespace vnqa
 
 using namespace vnqa;
@@ -102,12 +119,14 @@ extern "C" int vnqa_sumsq_partials(const float* g, int64_t n, double* partials, 
   return 0;
 }
 
-extern "C" int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const double* partials,
-                              int32_t n_partials, float grad_scale, float max_norm, double lr, double beta1,
-                              double beta2, double eps, int64_t step, float* norm_out, void* stream) {
-  // scalar coefficients exactly as torch.optim.Adam forms them: in double on the host, rounded to fp32 once
-  VNQA_REQUIRE(step >= 1, "vnqa_clip_adam: step counts from 1");
-  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+static int clip_adam_launch(float* p, const float* g, float* m, float* v, int64_t n, const double* partials,
+                            int32_t n_partials, float grad_scale, float max_norm, double lr, double beta1, double beta2,
+                            double eps, int64_t step, long long* step_dev, float* norm_out, void* stream) {
+  // scalar coefficients exactly as torch.optim.Adam forms them: in double (on the host, or by the kernel from the
+  // device-resident step count), rounded to fp32 once
+  VNQA_REQUIRE(step_dev != nullptr || step >= 1, "vnqa_clip_adam: step counts from 1");
+  const double tt = step_dev ? 1.0 : (double)step;
+  const double bc1 = 1.0 - pow(beta1, tt), bc2 = 1.0 - pow(beta2, tt);
   const float step_size = (float)(lr / bc1), bias_correction2_sqrt = (float)sqrt(bc2);
   const float w1 = (float)(1.0 - beta1), w2 = (float)(1.0 - beta2);
   VNQA_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0, "vnqa_clip_adam: need non-empty buffers of 4k floats");
@@ -119,7 +138,24 @@ extern "C" int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int6
   clip_adam_kernel<<<sms * 8, OPT_THREADS, 0, as_stream(stream)>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), n / 4, partials, n_partials, grad_scale, max_norm, step_size, (float)beta2, w1, w2,
-      (float)eps, bias_correction2_sqrt, norm_out);
+      (float)eps, bias_correction2_sqrt, norm_out, step_dev, lr, beta1, beta2);
   VNQA_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int vnqa_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, const double* partials,
+                              int32_t n_partials, float grad_scale, float max_norm, double lr, double beta1,
+                              double beta2, double eps, int64_t step, float* norm_out, void* stream) {
+  return clip_adam_launch(p, g, m, v, n, partials, n_partials, grad_scale, max_norm, lr, beta1, beta2, eps, step,
+                          nullptr, norm_out, stream);
+}
+
+extern "C" int vnqa_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const double* partials,
+                                  int32_t n_partials, float grad_scale, float max_norm, double lr, double beta1,
+                                  double beta2, double eps, int64_t* step_dev, float* norm_out, void* stream) {
+  VNQA_REQUIRE(step_dev != nullptr, "vnqa_clip_adam_dev: null step counter");
+  adam_step_inc_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<long long*>(step_dev));
+  VNQA_CHECK_CUDA(cudaGetLastError());
+  return clip_adam_launch(p, g, m, v, n, partials, n_partials, grad_scale, max_norm, lr, beta1, beta2, eps, 0,
+                          reinterpret_cast<long long*>(step_dev), norm_out, stream);
 }

@@ -58,7 +58,9 @@ class FusedClipAdam(torch.optim.Adam):
     backward write its gradients into the flat bucket (no per-tensor gradient allocations, nothing to pack for the
     all-reduce); without it ``step()`` gathers ``p.grad`` into the bucket first."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, capturable=False):
+        """capturable: keep the step count on the device (csrc/optim.cu vnqa_clip_adam_dev) so that ``step()`` does not
+        depend on host state and can be captured in a CUDA graph (videonavqa_b200.graph)."""
         params = list(params)
         super().__init__(params, lr=lr, betas=betas, eps=eps)
         if len(self.param_groups) != 1:
@@ -73,6 +75,8 @@ class FusedClipAdam(torch.optim.Adam):
         self._partials = torch.zeros(self._n_partials, device=dev, dtype=torch.float64)
         self._norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self._module = None
+        self.capturable = bool(capturable)
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int64) if self.capturable else None
         self._install_state()
 
     # ---- state plumbing ---------------------------------------------------------------------------------------
@@ -95,7 +99,17 @@ class FusedClipAdam(torch.optim.Adam):
                     self._v[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
                     steps = max(steps, int(float(st["step"])))
         self._steps = steps
+        if self.capturable:
+            self._step_dev.fill_(steps)
         self._install_state()
+
+    def state_dict(self):
+        if self.capturable:
+            # the count lives on the device (graph replays do not run Python): refresh the standard entries
+            self._steps = int(self._step_dev.item())
+            for p in self.flat.params:
+                self.state[p]["step"] = torch.tensor(float(self._steps))
+        return super().state_dict()
 
     def attach(self, module):
         """Route the module's backward into the gradient bucket (engine.GradSink) and let step() invalidate the
@@ -136,18 +150,22 @@ class FusedClipAdam(torch.optim.Adam):
                 torch._foreach_copy_(views, grads)
         g = self.param_groups[0]
         beta1, beta2 = g["betas"]
-        self._steps += 1
-        t = self._steps
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         L = _lib.lib()
         P = lambda x: ctypes.c_void_p(x.data_ptr())     # noqa: E731
         if self.max_norm > 0:
             _lib.check(L.vnqa_sumsq_partials(P(f.grad), f.total, P(self._partials), st), "vnqa_sumsq_partials")
-        _lib.check(L.vnqa_clip_adam(P(f.param), P(f.grad), P(self._m), P(self._v), f.total, P(self._partials),
-                                    self._n_partials, 1.0, self.max_norm, g["lr"], beta1, beta2, g["eps"], t,
-                                    P(self._norm), st), "vnqa_clip_adam")
-        for p in f.params:
-            self.state[p]["step"] += 1
+        if self.capturable:
+            _lib.check(L.vnqa_clip_adam_dev(P(f.param), P(f.grad), P(self._m), P(self._v), f.total, P(self._partials),
+                                            self._n_partials, 1.0, self.max_norm, g["lr"], beta1, beta2, g["eps"],
+                                            P(self._step_dev), P(self._norm), st), "vnqa_clip_adam_dev")
+        else:
+            self._steps += 1
+            _lib.check(L.vnqa_clip_adam(P(f.param), P(f.grad), P(self._m), P(self._v), f.total, P(self._partials),
+                                        self._n_partials, 1.0, self.max_norm, g["lr"], beta1, beta2, g["eps"],
+                                        self._steps, P(self._norm), st), "vnqa_clip_adam")
+            for p in f.params:
+                self.state[p]["step"] += 1
         if self._module is not None:
             self._module.invalidate_weight_cache(registered_only=True)
             self._module._bucket_filled = False
