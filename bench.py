@@ -766,11 +766,13 @@ def gpu_leg(args):
         g1.record()
         host_s = time.perf_counter() - t0
         torch.cuda.synchronize()
-        # host time of the eager loop for comparison: enqueue only, no synchronisation inside
-        t0 = time.perf_counter()
+        # host time of one eager step for comparison: enqueue only, starting from an empty GPU queue
+        eager_host_s = 0.0
         for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             step(*dev_in)
-        eager_host_s = (time.perf_counter() - t0) / 3
+            eager_host_s += (time.perf_counter() - t0) / 3
         torch.cuda.synchronize()
         graph_info = {"ms_per_step": round(g0.elapsed_time(g1) / args.steps, 3),
                       "host_ms_per_replay": round(host_s / args.steps * 1e3, 3),

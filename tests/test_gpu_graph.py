@@ -3,8 +3,11 @@
 Two identical modules take the same three different batches (tokens, question lengths, frames and labels change; the
 clip-length pattern is the graph's identity): one through ``GraphedTrainStep.__call__`` (graph replays only), one
 through the eager loop body of eval/q_and_v_eval.py:119-139.  Losses, every parameter, both Adam moments, the BatchNorm
-running statistics and the optimizer's step count must agree; the only non-bit-exact pieces of the step are the
-atomic accumulations of the BatchNorm sums (fp64) and bias gradients, hence 1e-5 instead of equality.
+running statistics and the optimizer's step count must agree.  The only non-bit-exact pieces of the step are the
+atomic accumulations of the BatchNorm sums (fp64) and bias gradients, and Adam turns last-bit differences of near-zero
+gradient elements into +-lr differences of single weights (m / sqrt(v) is a sign function there - the same holds
+between two eager runs).  The comparison is therefore made on ONE step from an identical state: loss, the whole
+gradient bucket, both moments and the BatchNorm statistics to 1e-5; further replays are checked through their losses.
 """
 import pytest
 import torch
@@ -39,36 +42,54 @@ def test_graph_replay_matches_eager_steps(case):
     v_lens = b["v_lens"].clone()                      # CPU tensor: the graph's identity
 
     me, oe = _build(kind, kw, params, capturable=False)
-    loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
-    eager_losses = []
-    for v, q, ql, y in batches:
-        me.init_hidden()
-        loss = loss_fn(me(v, q, v_lens, ql), y)
-        loss.backward()
-        oe.step()
-        oe.zero_grad()
-        eager_losses.append(float(loss))
-
     mg, og = _build(kind, kw, params, capturable=True)
+    loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
+
+    def eager(m, o, v, q, ql, y):
+        m.init_hidden()
+        loss = loss_fn(m(v, q, v_lens, ql), y)
+        loss.backward()
+        o.step()
+        o.zero_grad()
+        return loss
+
+    # both modules first train one step EAGERLY on the default stream, and the graphed one keeps its loss tensor (and
+    # with it the autograd graph) alive - the situation of a training script that switches to graph replay later
+    stale = [eager(me, oe, *batches[0]), eager(mg, og, *batches[0])]
+    assert abs(float(stale[0].detach()) - float(stale[1].detach())) <= 1e-5 * abs(float(stale[0].detach()))
     before = [p.detach().clone() for p in mg.parameters()]
+    n_tracked = int(mg.bn_init.num_batches_tracked)
     step = GraphedTrainStep(mg, og, *batches[0][:2], v_lens, *batches[0][2:], loss_fn=loss_fn)
     # capturing (and its eager warm-up steps) must leave the training state untouched
     assert all(torch.equal(p, q) for p, q in zip(mg.parameters(), before))
-    assert int(og._step_dev.item()) == 0 and int(mg.bn_init.num_batches_tracked) == 0
-    graph_losses = [float(step(v, q, ql, y)) for v, q, ql, y in batches]
+    assert int(og._step_dev.item()) == 1 and int(mg.bn_init.num_batches_tracked) == n_tracked
 
-    for a, c in zip(eager_losses, graph_losses):
-        assert abs(a - c) <= 1e-5 * max(1.0, abs(a)), (eager_losses, graph_losses)
-    assert len({round(x, 4) for x in graph_losses}) == 3                 # the replays really saw three different batches
-    for (n, p), q in zip(me.named_parameters(), mg.parameters()):
-        assert float((p - q).abs().max()) <= 1e-5 * max(1e-3, float(p.abs().max())), n
-    assert float((oe._m - og._m).abs().max()) <= 1e-5 * float(oe._m.abs().max())
-    assert float((oe._v - og._v).abs().max()) <= 1e-5 * float(oe._v.abs().max())
+    # identical starting state (the two eager first steps already differ in single weights: Adam turns last-bit
+    # differences of near-zero gradient elements - atomics - into +-lr), then ONE step each on a new batch
+    with torch.no_grad():
+        og.flat.param.copy_(oe.flat.param); og._m.copy_(oe._m); og._v.copy_(oe._v)
+        for (_, a), (_, c) in zip(me.named_buffers(), mg.named_buffers()):
+            c.copy_(a)
+    # (conv1x1_layers are never optimised - quirk Q1 - and identical in both modules by construction)
+    le = float(eager(me, oe, *batches[1]).detach())
+    lg = float(step(*batches[1]))
+    assert abs(le - lg) <= 1e-5 * abs(le), (le, lg)
+
+    def rel(a, c):
+        return float((a.double() - c.double()).norm() / a.double().norm().clamp_min(1e-30))
+    assert rel(oe.flat.grad, og.flat.grad) <= 1e-5          # the gradient bucket of the step (kept until the next backward)
+    assert rel(oe._m, og._m) <= 1e-5 and rel(oe._v, og._v) <= 1e-5
     assert torch.allclose(me.bn_init.running_mean, mg.bn_init.running_mean, rtol=1e-5, atol=1e-7)
     assert torch.allclose(me.bn_init.running_var, mg.bn_init.running_var, rtol=1e-5, atol=1e-7)
+    for ca, cc in zip(me.conv1x1_layers, mg.conv1x1_layers):          # Q1: unregistered, but they do receive .grad
+        assert cc.weight.grad is not None and rel(ca.weight.grad, cc.weight.grad) <= 1e-5
+
+    # further replays really see new inputs, and the bookkeeping that no Python runs for stays right
+    losses = [(float(eager(me, oe, *bt).detach()), float(step(*bt))) for bt in (batches[2], batches[0])]
+    assert all(abs(a - c) <= 2e-3 * abs(a) for a, c in losses), losses
+    assert len({round(c, 3) for _, c in losses} | {round(lg, 3)}) == 3
     assert int(me.bn_init.num_batches_tracked) == int(mg.bn_init.num_batches_tracked)
-    sd = og.state_dict()
-    assert float(sd["state"][0]["step"]) == 3.0 == float(oe.state_dict()["state"][0]["step"])
+    assert float(og.state_dict()["state"][0]["step"]) == 4.0 == float(oe.state_dict()["state"][0]["step"])
 
 
 def test_capturable_adam_matches_host_step_count():

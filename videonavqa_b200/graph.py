@@ -6,6 +6,9 @@ the launch geometry on the host, so it is part of the graph's identity; question
 device data and may change between replays).  Replaying it issues the ~300 kernel launches of the step with a single
 driver call: no Python, no ctypes, no tensor-map encoding, no allocator traffic.
 
+The unregistered ``conv1x1_layers`` (quirk Q1: no optimizer ever updates them) are frozen into the graph through their
+packed copies; re-capture after changing them by hand.
+
 Requirements: ``FusedClipAdam(..., capturable=True).attach(model)`` (step count on the device, gradients in the flat
 bucket), the attention or global-pooling model (the multi-hop model sizes a kernel by the longest question on the
 host), a single GPU per graph.  Everything the step touches keeps its address: parameters and moments are flat buffers,

@@ -36,16 +36,17 @@ class _FilmFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, need_grad, v_input, q_input, v_lens, q_lens, *params):
         ctx.set_materialize_grads(False)
-        P = dict(zip(mod._param_names, params))
+        P = dict(zip(mod._param_names, params))            # a trailing autograd anchor (bucket mode) is not a parameter
         logits, saved = mod._forward_impl(P, v_input, q_input, v_lens, q_lens, save=need_grad)
         ctx.mod, ctx.saved, ctx.P = mod, saved, P
+        ctx.n_inputs = 6 + len(params)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         mod = ctx.mod
         if dlogits is None:
-            return (None,) * (6 + len(mod._param_names))
+            return (None,) * ctx.n_inputs
         bucket = getattr(mod, "_grad_bucket", None)
         if bucket:
             # flat-bucket mode (videonavqa_b200.optim.FlatBuffers): one memset, the kernels write every registered
@@ -59,16 +60,21 @@ class _FilmFunction(torch.autograd.Function):
         out = []
         for n in mod._param_names:
             g = grads.get(n)
-            if bucket and n in bucket and g is not None:
+            if bucket and g is not None:
                 # p.grad IS the bucket slice (no copy by AccumulateGrad).  Overwrite semantics: the reference zeroes
                 # the gradients every iteration (eval/q_and_v_eval.py:139); accumulation across backward calls is
-                # not supported in this mode.
-                ctx.P[n].grad = bucket[n]
+                # not supported in this mode.  The unregistered conv1x1_layers (Q1: never optimised, but they do
+                # receive .grad) get theirs assigned the same way.  Autograd sees none of the parameters in this mode
+                # (forward() hands detached aliases + a fresh anchor leaf to this node): their AccumulateGrad nodes
+                # remember the stream they were first used on and make the engine synchronise with it after every
+                # backward, which is illegal while a CUDA graph is being captured on another stream
+                # (videonavqa_b200.graph) if the module has trained eagerly before.
+                mod._leaf_params[n].grad = bucket[n] if n in bucket else g
                 g = None
             out.append(g)
         if bucket:
             mod._bucket_filled = True
-        return (None,) * 6 + tuple(out)
+        return (None,) * 6 + tuple(out) + (None,) * (ctx.n_inputs - 6 - len(out))
 
 
 def check_channels(num_input_channels, num_res_block_channels, hidden_size):
@@ -135,6 +141,13 @@ class FilmModuleBase(nn.Module):
         names, tensors = self._collect_params()
         self._param_names = names
         need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        if need_grad and getattr(self, "_grad_bucket", None):
+            # flat-bucket mode: backward assigns every .grad itself (see _FilmFunction.backward); the node hangs off a
+            # fresh scalar leaf so that loss.backward() reaches it
+            self._leaf_params = dict(zip(names, tensors))
+            anchor = torch.zeros((), device=v_input.device, requires_grad=True)
+            return _FilmFunction.apply(self, need_grad, v_input.float(), q_input, v_lens, q_lens,
+                                       *[t.detach() for t in tensors], anchor)
         return _FilmFunction.apply(self, need_grad, v_input.float(), q_input, v_lens, q_lens, *tensors)
 
     def _host_lens(self, v_lens, q_lens, dev):
