@@ -753,6 +753,14 @@ def gpu_leg(args):
     graph_info = None
     if args.graph and world == 1 and fused and args.model != "tmh":
         from videonavqa_b200.graph import GraphedTrainStep
+        # host time of one eager step for comparison: enqueue only, starting from an empty GPU queue
+        eager_host_s = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step(*dev_in)
+            eager_host_s = min(eager_host_s, time.perf_counter() - t0)
+        torch.cuda.synchronize()
         gstep = GraphedTrainStep(model, opt, dev_in[0], dev_in[1], host[2], dev_in[3], dev_in[4],
                                  loss_fn=torch.nn.CrossEntropyLoss(reduction="sum"))
         for _ in range(2):
@@ -765,14 +773,6 @@ def gpu_leg(args):
             gstep()
         g1.record()
         host_s = time.perf_counter() - t0
-        torch.cuda.synchronize()
-        # host time of one eager step for comparison: enqueue only, starting from an empty GPU queue
-        eager_host_s = 0.0
-        for _ in range(3):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            step(*dev_in)
-            eager_host_s += (time.perf_counter() - t0) / 3
         torch.cuda.synchronize()
         graph_info = {"ms_per_step": round(g0.elapsed_time(g1) / args.steps, 3),
                       "host_ms_per_replay": round(host_s / args.steps * 1e3, 3),
