@@ -45,8 +45,8 @@ MODELS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", choices=["train", "eval", "stem"], default="train",
                     help="train / eval = the FiLM path (headline); stem = the frozen ObjDetectCNN in front of it "
                          "(SURVEY 8(f) rank 2), 35 per-frame calls per step as the drivers issue them")
