@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--run-ahead", type=int, default=int(os.environ.get("BENCH_RUN_AHEAD", "0")),
                     help="device-resident loop: the host may be at most this many steps ahead of the GPU (it waits on the "
                          "event of step i - K before enqueuing step i + 1; 0 = unbounded).  The GPU queue never drains.")
+    ap.add_argument("--stem-frames", type=int, default=0,
+                    help="--workload stem: frame images per call (default: the batch size = one call per frame as the "
+                         "drivers do; batch*35 = the whole clip batch in one call)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="skip the extra leg that captures the train step in a CUDA graph (videonavqa_b200.graph) and "
                          "times its replays (single GPU, attn / gp, fused optimizer; reported as `cuda_graph`, the "
@@ -388,10 +391,14 @@ def stem_leg(args):
             bn.weight.normal_(0.8, 0.3); bn.bias.normal_(0, 0.3)
             bn.running_mean.normal_(0, 0.4); bn.running_var.uniform_(0.5, 2.0)
     m._weight_cache.invalidate()
-    NBUF = 4                                    # distinct per-frame inputs, cycled (4 x 68 MB pinned)
-    host = [torch.randn(B, 128, 40, 52).clamp_min_(0).pin_memory() for _ in range(NBUF)]
+    F = args.stem_frames or B                   # frame images per call
+    assert (B * T) % F == 0, "--stem-frames must divide batch * 35"
+    CALLS = B * T // F
+    NBUF = 4 if F <= 256 else 1                 # distinct inputs, cycled (4 x 68 MB pinned at F = 64)
+    host = [torch.randn(F, 128, 40, 52).clamp_min_(0).pin_memory() for _ in range(NBUF)]
     dev_in = [h.to(dev) for h in host]
-    h2d = T * host[0].numel() * 4
+    h2d = CALLS * host[0].numel() * 4
+    T_CLIP, T = T, CALLS                        # the loops below issue CALLS calls per step
 
     def step(fetch):
         y = None
@@ -479,10 +486,11 @@ def stem_leg(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16 operands, fp32 accumulate" if fp16 else "tf32 operands, fp32 accumulate", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_step": B * T, "gflop_per_frame": round(gflop_frame, 3),
+        "config": {"workload": workload_name(args), "frames_per_step": B * T_CLIP, "frames_per_call": F,
+                   "calls_per_step": CALLS, "gflop_per_frame": round(gflop_frame, 3),
                    "l2": "inputs larger than L2 (68 MB per call in, 136 MB intermediates)"},
-        "frames_per_s": round(B * T / (ms * 1e-3), 1),
-        "model_tflops": round(B * T * gflop_frame / ms, 1),
+        "frames_per_s": round(B * T_CLIP / (ms * 1e-3), 1),
+        "model_tflops": round(B * T_CLIP * gflop_frame / ms, 1),
         "e2e": {"value": round(B / (e2e_ms * 1e-3), 2), "unit": "clips/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_ms, 3),
                 "how": "each call's (B,128,40,52) input copied from pinned host memory through a double buffer on a "
@@ -496,7 +504,7 @@ def stem_leg(args):
     }
     if not args.no_eager:
         try:
-            out["gpu_eager_baseline"] = eager_stem_leg(dev, dev_in, T)
+            out["gpu_eager_baseline"] = eager_stem_leg(dev, dev_in, CALLS)
         except Exception as e:  # noqa: BLE001
             out["gpu_eager_baseline"] = {"error": repr(e)[:200]}
     return out
@@ -508,7 +516,7 @@ def eager_stem_leg(dev, dev_in, T, steps=2):
     import torch
     from oracle import stem_oracle as S
     B = dev_in[0].shape[0]
-    out = {"what": "PyTorch eager on the same GPU, 35 per-frame calls per step", "batch": B}
+    out = {"what": f"PyTorch eager on the same GPU, the same {T} call(s) of {B} frame images per step", "batch": B}
     if os.path.exists(STEM_REF):
         ref = _load_reference_stem().to(dev)
         out["impl"] = "the reference's own ObjDetectCNN"

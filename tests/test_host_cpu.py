@@ -185,6 +185,21 @@ def test_frozen_stem_module_surface(golden_dir):
         m.eval()(torch.zeros(1, 128, 40, 52))
 
 
+def test_q8_embedding_padding_idx_matches_the_reference():
+    """Quirk Q8: the attention model's embedding has NO padding_idx (film_attn_pt_stem.py:37: row 0 is an ordinary,
+    randomly initialised row), the global-pooling and multi-hop models use padding_idx=0 (row 0 zero, no gradient)
+    (film_global_pooling_pt_stem.py:34, time_multi_hop_pt_stem.py:30)."""
+    from videonavqa_b200.models import (FiLMAttnPretrainedStem, FiLMGlobalPoolingPretrainedStem,
+                                        TimeMultiHopFiLMPretrainedStem)
+    kw = dict(num_input_channels=32, num_res_block_channels=32, hidden_size=32, vocab_size=20)
+    a = FiLMAttnPretrainedStem(2, 16, 7, at_hidden_size=32, **kw)
+    g = FiLMGlobalPoolingPretrainedStem(2, 16, 7, num_tail_channels=8, **kw)
+    t = TimeMultiHopFiLMPretrainedStem(2, 16, 7, num_tail_channels=8, **kw)
+    assert a.embed.padding_idx is None and float(a.embed.weight[0].abs().sum()) > 0
+    for m in (g, t):
+        assert m.embed.padding_idx == 0 and float(m.embed.weight[0].abs().sum()) == 0.0
+
+
 def test_constructor_validates_kernel_constraints():
     from videonavqa_b200.models import FiLMAttnPretrainedStem
     with pytest.raises(ValueError, match="multiples of 32"):
