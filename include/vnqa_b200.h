@@ -69,6 +69,13 @@ int vnqa_to_half(const float* in, void* out, int64_t n, float scale, void* strea
 int vnqa_permute_fc_weight(const float* w, float* out, int32_t n, int32_t n_pad, int32_t C, int32_t inverse,
                            void* stream);
 
+/* ---- data path (eval/dataset.py:57-93 + the .float() of q_and_v_eval.py:93):
+ * frames [B][T][H][W][3] uint8 (decoded frames as OpenCV delivers them, already subsampled, zero frames behind each
+ * clip's end)  ->  out (B, 3, H, W, T) fp32 with out = lut256[u8]; lut256[i] = (float)((double)i / 255.0) makes it
+ * bit-identical to the reference's float64 division and cast. */
+int vnqa_frames_u8_to_video(const uint8_t* frames, float* out, const float* lut256, int32_t B, int32_t T, int32_t H,
+                            int32_t W, void* stream);
+
 /* ---- K1/K2/K3: implicit-GEMM convolution / GEMM on tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM).
  * D[co][pixel] = sum_{tap,ci} Wp[tap][co][ci] * X[pixel + tap][ci], 128 x 208 tiles (208 = 8 images x 2 rows x 13),
  * operands staged by TMA (the zero halo is the TMA out-of-bounds fill), fused epilogues below. */

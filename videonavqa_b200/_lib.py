@@ -51,6 +51,7 @@ SIGNATURES = {
     "vnqa_debug_build": [],
     "vnqa_frames_to_nhwc": [P, P, P, I32, I32, I32, I32, P],
     "vnqa_frames_blocked_to_nhwc": [P, P, P, I32, I32, I32, I64, I64, I32, P],
+    "vnqa_frames_u8_to_video": [P, P, P, I32, I32, I32, I32, P],
     "vnqa_pack_conv_weight": [P, P, I32, I32, I32, I32, I32, I32, P],
     "vnqa_to_half": [P, P, I64, F32, P],
     "vnqa_permute_fc_weight": [P, P, I32, I32, I32, I32, P],

@@ -1,0 +1,71 @@
+// Data path, first device-side slice (replaces the numpy staging of eval/dataset.py:57-93).
+//
+// The reference decodes a clip with OpenCV into an np.empty((3, 160, 208, 400)) float64 array (320 MB per clip), copies
+// the 1-of-4 subsampled frames into a second float64 array, divides by 255 and hands (3, 160, 208, 35) float64 per clip
+// to the DataLoader; the driver casts the batch to fp32 on the way to the GPU (q_and_v_eval.py:93,98).  Here the decoded
+// frames stay uint8: the loader gathers the selected frames of a batch into ONE pinned buffer [B][T][H][W][3] (BGR as
+// OpenCV delivers it, zero frames behind each clip's end), 1 byte per sample crosses PCIe instead of 4, and this kernel
+// produces the tensor the drivers index, video[b][c][h][w][t] = fp32(double(u8) / 255.0), in one pass.  The division
+// goes through a 256-entry table computed in double on the host, so the result is bit-identical to the reference's
+// float64 division followed by .float().
+//
+// One block per (clip, image row): the T x W x 3 bytes of that row are staged in shared memory (reads of W*3 = 624
+// contiguous bytes per frame), then every channel's (w, t) plane - W*T contiguous floats in the output - is written
+// with consecutive threads on consecutive addresses.
+#include "common.h"
+
+namespace vnqa {
+
+__global__ void __launch_bounds__(256) frames_u8_to_video_kernel(const uint8_t* __restrict__ frames,
+                                                                 float* __restrict__ out,
+                                                                 const float* __restrict__ lut, int T, int H, int W) {
+  extern __shared__ uint8_t row[];            // [T][W*3]
+  __shared__ float s_lut[256];
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int w3 = W * 3;
+  s_lut[threadIdx.x] = __ldg(lut + threadIdx.x);
+  // stage: frame t, row h -> row[t][:]; 4-byte loads when the row length allows (W*3 = 624)
+  const long long frame_stride = (long long)H * w3;
+  const uint8_t* src0 = frames + (long long)b * T * frame_stride + (long long)h * w3;
+  if ((w3 & 3) == 0 && (reinterpret_cast<uintptr_t>(frames) & 3) == 0) {
+    const int n4 = w3 >> 2;
+    for (int i = threadIdx.x; i < T * n4; i += blockDim.x) {
+      const int t = i / n4, j = i - t * n4;
+      reinterpret_cast<uint32_t*>(row)[i] = __ldg(reinterpret_cast<const uint32_t*>(src0 + t * frame_stride) + j);
+    }
+  } else {
+    for (int i = threadIdx.x; i < T * w3; i += blockDim.x) {
+      const int t = i / w3, j = i - t * w3;
+      row[i] = __ldg(src0 + t * frame_stride + j);
+    }
+  }
+  __syncthreads();
+  const int plane = W * T;                    // contiguous floats of one (clip, channel, row) in the output
+  for (int c = 0; c < 3; ++c) {
+    float* dst = out + (((long long)b * 3 + c) * H + h) * plane;
+    for (int i = threadIdx.x; i < plane; i += blockDim.x) {
+      const int w = i / T, t = i - w * T;
+      dst[i] = s_lut[row[t * w3 + w * 3 + c]];
+    }
+  }
+}
+
+}  // namespace vnqa
+
+using namespace vnqa;
+
+extern "C" int vnqa_frames_u8_to_video(const uint8_t* frames, float* out, const float* lut256, int32_t B, int32_t T,
+                                       int32_t H, int32_t W, void* stream) {
+  VNQA_REQUIRE(frames && out && lut256, "vnqa_frames_u8_to_video: null pointer");
+  VNQA_REQUIRE(B > 0 && B <= 65535 && T > 0 && H > 0 && W > 0, "vnqa_frames_u8_to_video: bad sizes (%d, %d, %d, %d)", B, T, H, W);
+  const size_t smem = ((size_t)T * W * 3 + 3) & ~size_t(3);
+  VNQA_REQUIRE(smem <= 200 * 1024, "vnqa_frames_u8_to_video: T*W*3 = %zu bytes do not fit in shared memory", smem);
+  static size_t max_smem = 48 * 1024;
+  if (smem > max_smem) {
+    VNQA_CHECK_CUDA(cudaFuncSetAttribute(frames_u8_to_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_smem = smem;
+  }
+  frames_u8_to_video_kernel<<<dim3(H, B), 256, smem, as_stream(stream)>>>(frames, out, lut256, T, H, W);
+  VNQA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
