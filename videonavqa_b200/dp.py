@@ -182,9 +182,11 @@ class FlatReducer:
     """Installs itself as the module's gradient hook (engine.GradSink).  ``wait()`` is called by the autograd node at
     the end of backward: after it returns (on the compute stream) the flat gradient bucket holds the SUM over ranks."""
 
-    def __init__(self, module, flat, overlap=None, min_bytes=16 << 20):
+    def __init__(self, module, flat, overlap=None, min_bytes=None):
         self.flat = flat
         self.overlap = (os.environ.get("VNQA_DP_OVERLAP", "1") == "1") if overlap is None else overlap
+        if min_bytes is None:        # slice size from which the frontier is handed to NCCL (VNQA_DP_MIN_MB to tune)
+            min_bytes = int(float(os.environ.get("VNQA_DP_MIN_MB", "16")) * (1 << 20))
         self.min_elems = max(1, min_bytes // 4)
         names = {id(p): n for n, p in module.named_parameters()}
         self.index = {names[id(p)]: i for i, p in enumerate(flat.params) if id(p) in names}
