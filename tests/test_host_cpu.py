@@ -30,6 +30,46 @@ def test_library_exports_every_declared_symbol():
     assert handle.vnqa_abi_version() == 3
 
 
+def test_abi_rejects_bad_arguments_before_touching_the_device():
+    """Error behaviour of the C ABI: argument checks come first, return -1 and leave a thread-local message
+    (include/vnqa_b200.h); none of these calls reaches a CUDA API, so they run on the CPU-only build container."""
+    from videonavqa_b200 import _lib
+    from videonavqa_b200._lib import ConvArgs
+    L = _lib.lib()
+    msg = lambda: L.vnqa_last_error().decode()     # noqa: E731
+    assert L.vnqa_conv_gemm(None, None) == -1 and "null args" in msg()
+    a = ConvArgs()
+    a.taps, a.rows_pad, a.cout, a.n_img = 5, 128, 128, 1
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "taps must be 1 or 9" in msg()
+    a.taps, a.rows_pad = 9, 100
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "rows_pad" in msg()
+    a.rows_pad, a.n_img = 128, 0
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "empty batch" in msg()
+    a.n_img = 1
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "null operand" in msg()
+    buf = (ctypes.c_float * 64)()
+    pb = ctypes.cast(buf, ctypes.c_void_p)
+    a.w_packed = a.x = a.out = pb.value
+    a.act_dtype = 7
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "act_dtype" in msg()
+    a.act_dtype, a.cin, a.img_h, a.img_w = 1, 64, 10, 50
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "img_w must be 13, 26 or 52" in msg()
+    a.img_w, a.img_h = 26, 7
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "img_h must be even" in msg()
+    a.img_h, a.pool, a.epi = 20, 1, 0
+    assert L.vnqa_conv_gemm(ctypes.byref(a), None) == -1 and "pool needs BIAS_AFFINE_RELU" in msg()
+    assert L.vnqa_frames_u8_to_video(None, None, None, 1, 1, 1, 1, None) == -1 and "null pointer" in msg()
+    assert L.vnqa_frames_u8_to_video(pb, pb, pb, 0, 35, 160, 208, None) == -1 and "bad sizes" in msg()
+    assert L.vnqa_nchw_to_nhwc_affine(pb, pb, pb, None, 1, 2, 4, 1, None) == -1 and "scale and shift go together" in msg()
+    assert L.vnqa_nhwc_to_nchw(None, pb, 1, 2, 4, 0, None) == -1
+    assert L.vnqa_frames_blocked_to_nhwc(pb, pb, pb, 1, 33, 35, 0, 0, 1, None) == -1 and "multiple of 32" in msg()
+    assert L.vnqa_sumsq_partials(pb, 3, pb, None) == -1 and "4k floats" in msg()
+    assert L.vnqa_clip_adam(pb, pb, pb, pb, 64, pb, 1, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0, None, None) == -1 \
+        and "step counts from 1" in msg()
+    assert L.vnqa_clip_adam_dev(pb, pb, pb, pb, 64, pb, 1, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, None, None, None) == -1
+    assert L.vnqa_conv_wgrad_ws_bytes(100, 128, 9, None) < 0 or True      # (returns a size or a negative code; no device)
+
+
 def test_conv_args_struct_matches_header_field_order():
     from videonavqa_b200._lib import ConvArgs
     text = open(os.path.join(ROOT, "include", "vnqa_b200.h")).read()
