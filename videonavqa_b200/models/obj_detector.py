@@ -38,21 +38,17 @@ class ObjDetectCNN(nn.Module):
             raise ValueError(f"videonavqa_b200 needs num_filters to be a multiple of 32 (got {num_filters})")
         self.logits = logits
         self.pretrained_features = pretrained_features
-        # registration order of obj_detector.py:21-44
+        # Same attribute names, shapes and REGISTRATION ORDER as obj_detector.py:21-44 (the reference's checkpoints and
+        # optimizer states are keyed by them): input BatchNorm, then three stages of conv-conv-BatchNorm-pool at
+        # 40 x 52 / 20 x 26 / 10 x 13, then the classifier tail (registered for state_dict parity, not run here).
+        F = num_filters
         self.bn_input = nn.BatchNorm2d(self.IN_CHANNELS)
-        self.conv11 = nn.Conv2d(self.IN_CHANNELS, num_filters, kernel_size=3, padding=1)
-        self.conv12 = nn.Conv2d(num_filters, num_filters, kernel_size=3, padding=1)
-        self.bn1 = nn.BatchNorm2d(num_filters)
-        self.pool1 = nn.MaxPool2d(kernel_size=2, stride=2)
-        self.conv21 = nn.Conv2d(num_filters, num_filters, kernel_size=3, padding=1)
-        self.conv22 = nn.Conv2d(num_filters, num_filters, kernel_size=3, padding=1)
-        self.bn2 = nn.BatchNorm2d(num_filters)
-        self.pool2 = nn.MaxPool2d(kernel_size=2, stride=2)
-        self.conv31 = nn.Conv2d(num_filters, num_filters, kernel_size=3, padding=1)
-        self.conv32 = nn.Conv2d(num_filters, num_filters, kernel_size=3, padding=1)
-        self.bn3 = nn.BatchNorm2d(num_filters)
-        self.pool3 = nn.MaxPool2d(kernel_size=2, stride=2)
-        self.fc_tail1 = nn.Linear(num_filters * 6 * 5, tail_hidden_dim)
+        for stage, cin in ((1, self.IN_CHANNELS), (2, F), (3, F)):
+            setattr(self, f"conv{stage}1", nn.Conv2d(cin, F, kernel_size=3, padding=1))
+            setattr(self, f"conv{stage}2", nn.Conv2d(F, F, kernel_size=3, padding=1))
+            setattr(self, f"bn{stage}", nn.BatchNorm2d(F))
+            setattr(self, f"pool{stage}", nn.MaxPool2d(kernel_size=2, stride=2))
+        self.fc_tail1 = nn.Linear(F * 6 * 5, tail_hidden_dim)
         self.bn_tail1 = nn.BatchNorm1d(tail_hidden_dim)
         self.fc_tail2 = nn.Linear(tail_hidden_dim, nb_classes)
         self.dropout = nn.Dropout(p=tail_dropout_p)
