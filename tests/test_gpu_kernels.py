@@ -75,6 +75,62 @@ def test_frames_to_nhwc_reads_the_drivers_frame_blocked_view_in_place(C):
                        ops.frames_to_nhwc(v3.contiguous(), plan.img_of, plan.n_img, 1))
 
 
+@pytest.mark.parametrize("act", [1, 0], ids=["fp16", "tf32"])
+@pytest.mark.parametrize("mask_relu", [True, False])
+def test_film_backward_kernel(act, mask_relu):
+    """Autograd of the FiLM modulation out = relu(alpha * z + beta) (+ res) (models/film_attn_pt_stem.py:229-239) at the
+    kernel level, both operand types: dz = alpha * dOut * [alpha z + beta > 0] (stored in the operand type),
+    dalpha / dbeta per (film row, channel) summed over the image's 130 pixels (masked where the generator's ReLU output
+    is 0 when mask_relu), dbias += sum of the STORED dz; everything that leaves the fp16 domain times grad_unscale."""
+    from videonavqa_b200 import ops
+    n_img, C, NB, k = 11, 256, 2, 1
+    g = torch.Generator(device="cuda").manual_seed(17 + act)
+    rows = 14                                                    # more film rows than images: rows are gathered
+    film = torch.randn(rows, 2 * C * NB, device="cuda", generator=g)
+    if mask_relu:
+        film.clamp_min_(0)                                       # the generator ends in a ReLU (:179)
+    film_row = torch.randperm(rows, device="cuda", generator=g)[:n_img].to(torch.int32)
+    z32 = torch.randn(n_img, 130, C, device="cuda", generator=g)
+    d32 = torch.randn(n_img, 130, C, device="cuda", generator=g) * 0.1
+    if act:
+        z, dout = z32.half(), d32.half()
+    else:
+        z, dout = O.tf32_round(z32), O.tf32_round(d32)
+    zf, df = z.float(), dout.float()
+    unscale = 0.25 if act else 1.0
+    dfilm = torch.zeros_like(film)
+    dbias0 = torch.randn(C, device="cuda", generator=g)
+    dbias = dbias0.clone()
+    dz = ops.film_backward(dout, z, film, film_row, 2 * k * C, dfilm, dbias, mask_relu=mask_relu, act=act,
+                           grad_unscale=unscale)
+    al = film[film_row.long(), 2 * k * C:(2 * k + 1) * C][:, None, :]
+    be = film[film_row.long(), (2 * k + 1) * C:(2 * k + 2) * C][:, None, :]
+    pre = al.double() * zf.double() + be.double()
+    # away from the ReLU edge the fused and the exact sign agree; exactly 0 (alpha = beta = 0 after the generator's
+    # ReLU) is on the 'off' side in both
+    safe = (pre.abs() > 1e-5) | (pre == 0)
+    dF = torch.where(pre > 0, df, torch.zeros_like(df))
+    want_dz = (al * dF).half().float() if act else O.tf32_round(al * dF)
+    assert dz.dtype == z.dtype
+    assert torch.equal(dz.float()[safe], want_dz[safe])
+    assert float((~safe).float().mean()) < 1e-3
+    da = (dF.double() * zf.double()).sum(1) * unscale
+    db = dF.double().sum(1) * unscale
+    if mask_relu:
+        da = torch.where(al[:, 0] > 0, da, torch.zeros_like(da))
+        db = torch.where(be[:, 0] > 0, db, torch.zeros_like(db))
+    got_a = dfilm[film_row.long(), 2 * k * C:(2 * k + 1) * C].double()
+    got_b = dfilm[film_row.long(), (2 * k + 1) * C:(2 * k + 2) * C].double()
+    assert float((got_a - da).abs().max()) <= 1e-4 * float(da.abs().max())
+    assert float((got_b - db).abs().max()) <= 1e-4 * float(db.abs().max())
+    # rows and blocks this call does not own stay untouched
+    other = torch.ones(rows, dtype=torch.bool, device="cuda")
+    other[film_row.long()] = False
+    assert float(dfilm[other].abs().max()) == 0.0 and float(dfilm[:, :2 * k * C].abs().max()) == 0.0
+    want_db = dbias0.double() + dz.double().sum((0, 1)) * unscale
+    assert float((dbias.double() - want_db).abs().max()) <= 1e-4 * float(want_db.abs().max())
+
+
 def test_sgemm_variants_match_fp64():
     from videonavqa_b200 import ops
     g = torch.Generator().manual_seed(0)
