@@ -89,3 +89,12 @@ def test_device_conversion_is_bit_identical_to_the_reference():
     st.put(1, full[:6], indices=[0])
     o2 = st.to_device().cpu()
     assert torch.equal(o2[1], D.clip_tensor(full[:6], [0])[0].float()) and torch.equal(o2[0], o[0])
+    # any other frame count / frame size goes through the generic kernel
+    st2 = data.VideoBatchStager(2, "cuda", max_frames=20, height=24, width=30)
+    small = rng.randint(0, 256, size=(50, 24, 30, 3)).astype(np.uint8)
+    n0 = st2.put(0, small, rng=random.Random(9))
+    n1 = st2.put(1, small[:3], indices=[2])
+    o3 = st2.to_device().cpu()
+    assert (n0, n1) == (13, 1) and o3.shape == (2, 3, 24, 30, 20)
+    assert torch.equal(o3[0], D.clip_tensor(small, data.subsample_indices(50, rng=random.Random(9)), max_frames=20)[0].float())
+    assert torch.equal(o3[1], D.clip_tensor(small[:3], [2], max_frames=20)[0].float())
