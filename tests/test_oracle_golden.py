@@ -120,3 +120,38 @@ def test_stem_oracle_matches_the_reference_module(golden_dir):
         ye = S.stem_forward(P, x, emulate=emulate).double()
         rel = float((ye - y64).norm() / y64.norm())
         assert 1e-5 < rel <= 1.5e-3, (emulate, rel)
+
+
+@pytest.mark.parametrize("name", ["attn_small", "gp_small", "tmh_small"])
+def test_oracle_size_independent_properties(name):
+    """Properties of the path that hold at any size (and that the full-size GPU tests rely on): in eval mode a clip's
+    logits depend on nothing but that clip (BatchNorm uses running statistics), frames behind v_len and tokens behind
+    q_len are never read, and - for the models whose question attention is masked by packing (attn, gp) - the question
+    padding length does not matter."""
+    kind, kw, params, _, b, _ = load_case(name)
+    B, H = kw["batch_size"], kw["hidden_size"]
+    C = kw["num_res_block_channels"]
+    fwd = O.FORWARDS[kind]
+
+    def run(v, q, v_lens, q_lens):
+        with torch.no_grad():
+            return fwd(params, O.new_bn_state(C), O.new_film_state(v.shape[0], H), v, q, v_lens, q_lens,
+                       training=False)[0]
+    base = run(b["v"], b["q"], b["v_lens"], b["q_lens"])
+    # (1) garbage in the frames behind each clip's end and in the tokens behind each question's end changes nothing
+    v2, q2 = b["v"].clone(), b["q"].clone()
+    for i in range(B):
+        v2[i, ..., int(b["v_lens"][i]):] = 123.0
+        q2[i, int(b["q_lens"][i]):] = 1 + (i % (kw["vocab_size"] - 1))
+    if kind != "tmh":            # the multi-hop decoder attends over pad positions too (quirk Q10)
+        assert torch.equal(run(v2, q2, b["v_lens"], b["q_lens"]), base)
+    else:
+        assert torch.equal(run(v2, b["q"], b["v_lens"], b["q_lens"]), base)
+    # (2) clip independence: replace the other clips' content (same lengths: the effective batch per frame is part of
+    # the reference's bookkeeping) and clip 0's logits stay put
+    v3, q3 = b["v"].clone(), b["q"].clone()
+    v3[1:] = torch.rand_like(v3[1:])
+    q3[1:] = torch.where(q3[1:] > 0, torch.randint_like(q3[1:], 1, kw["vocab_size"]), q3[1:])
+    out3 = run(v3, q3, b["v_lens"], b["q_lens"])
+    assert torch.allclose(out3[0], base[0], rtol=0, atol=2e-6 * float(base.abs().max()))
+    assert not torch.allclose(out3[1], base[1], atol=1e-3 * float(base.abs().max()))
