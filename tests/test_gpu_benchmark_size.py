@@ -192,3 +192,24 @@ def test_b64_train_step_vs_strict_fp32_oracle_on_gpu():
         _assert_rows(rows)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("operands", ["fp16", "tf32"])
+def test_b64_clip_permutation_equivariance(operands):
+    """Size-independent property at the benchmark shape: in eval mode every clip is processed independently
+    (tests/test_oracle_golden.py pins that for the oracle), so permuting the clips of a batch of equal-length clips
+    permutes the logits - through 2240 frame images, the frame-major image order, the question-length sort and the
+    attention tail.  Images land in different tiles and different CTAs after the permutation; the accumulation order
+    inside a tile does not depend on the image's position, so the agreement is to the last bit."""
+    B = 64
+    m = _module(B, 21, False).set_operands(operands)
+    v, q, v_lens, q_lens, _ = O.synthetic_batch(B, seed=22)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3))
+    vc = v.cuda()
+    with torch.no_grad():
+        m.init_hidden()
+        a = m(vc, q.cuda(), v_lens, q_lens)
+        m.init_hidden()
+        b = m(vc[perm.cuda()].contiguous(), q[perm].cuda(), v_lens[perm], q_lens[perm])
+    assert torch.equal(a[perm.cuda()], b)
+    assert not torch.equal(a, b)
