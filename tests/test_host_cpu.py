@@ -270,6 +270,21 @@ def test_bench_reference_arm_json_contract():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["vs_baseline"] is None
 
 
+def test_bench_reference_arm_stem_workload():
+    """The same contract for the frozen-stem workload (`--workload stem`): one call of the reference's ObjDetectCNN on
+    64 frame images per step, reported in clips/s at 35 frames per clip."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "stem",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and "frozen stem" in line["metric"] and line["unit"] == "clips/s"
+    assert line["value"] > 0 and "64 frame images" in line["cpu_baseline"]["sample"]
+    assert "models/obj_detector.py" in line["config"]["workload"]
+
+
 def test_header_is_valid_c_and_struct_matches_ctypes(tmp_path):
     """include/vnqa_b200.h must compile as plain C (the ABI has no C++ / torch types) and vnqa_conv_args must have
     the size and field offsets the ctypes mirror assumes."""
